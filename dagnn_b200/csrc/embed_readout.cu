@@ -1,0 +1,109 @@
+// Node encoder (embedding gather-sum) and graph readout (masked segment pool) kernels — both pure HBM/L2
+// streaming work: one coalesced pass, float4 where the layout allows.
+#include "common.cuh"
+
+namespace dagnn {
+
+// X[v,:] = T[x[v,0],:] + A[x[v,1],:] + P[min(depth[v],max_depth),:]      (ogbg-code/utils.py:26-28)
+// one warp per node, lanes stride the feature dimension (float4 when D % 4 == 0)
+template <bool VEC4>
+__global__ void __launch_bounds__(256) k_embed(const int64_t* __restrict__ x, const int64_t* __restrict__ depth,
+                                               const float* __restrict__ T, const float* __restrict__ A,
+                                               const float* __restrict__ P, int max_depth, int N, int D,
+                                               float* __restrict__ X, int64_t ldx) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int v = blockIdx.x * wpb + (threadIdx.x >> 5); v < N; v += gridDim.x * wpb) {
+    const long long t = x[2 * (size_t)v], a = x[2 * (size_t)v + 1];
+    long long dp = depth[v];
+    dp = dp > max_depth ? max_depth : dp;
+    const float* tr = T + (size_t)t * D;
+    const float* ar = A + (size_t)a * D;
+    const float* pr = P + (size_t)dp * D;
+    float* o = X + (size_t)v * ldx;
+    if (VEC4) {
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + c));
+        const float4 av = __ldg(reinterpret_cast<const float4*>(ar + c));
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(pr + c));
+        float4 r;
+        r.x = tv.x + av.x + pv.x; r.y = tv.y + av.y + pv.y; r.z = tv.z + av.z + pv.z; r.w = tv.w + av.w + pv.w;
+        *reinterpret_cast<float4*>(o + c) = r;
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) o[c] = __ldg(tr + c) + __ldg(ar + c) + __ldg(pr + c);
+    }
+  }
+}
+
+struct ReadoutArgs {
+  int nblocks, pool, B;
+  DagnnReadoutBlock blk[DAGNN_MAX_READOUT_BLOCKS];
+  const int* pos[DAGNN_MAX_DIRS];
+  const int* gptr;
+};
+
+// grid (B, nblocks, column chunks of 128): thread c owns one output column, walks the graph's node range.
+__global__ void __launch_bounds__(128) k_readout(const __grid_constant__ ReadoutArgs a, float* __restrict__ out, int64_t ldo) {
+  const int g = blockIdx.x;
+  const DagnnReadoutBlock& b = a.blk[blockIdx.y];
+  const int c = blockIdx.z * 128 + threadIdx.x;
+  if (c >= b.width) return;
+  const int v0 = a.gptr[g], v1 = a.gptr[g + 1];
+  const int* pos = b.index_mode ? a.pos[b.dir] : nullptr;
+  float acc = (a.pool == 0) ? -INFINITY : 0.f;
+  int cnt = 0;
+  int vb = v0, ve = v1;
+  if (b.filter == 2) vb = max(v0, v1 - 1);
+  if (b.filter == 3) ve = min(v1, v0 + 1);
+  for (int v = vb; v < ve; ++v) {
+    if (b.filter == 1 && b.filter_lvl[v] != 0) continue;
+    const size_t row = pos ? (size_t)pos[v] : (size_t)v;
+    const float h = b.src[row * b.ld + c];
+    acc = (a.pool == 0) ? fmaxf(acc, h) : acc + h;
+    ++cnt;
+  }
+  if (cnt == 0) acc = 0.f;
+  else if (a.pool == 1) acc = acc / (float)cnt;
+  out[(size_t)g * ldo + b.out_col + c] = acc;
+}
+
+}  // namespace dagnn
+
+using namespace dagnn;
+
+extern "C" int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
+                               const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* stream_) {
+  DAGNN_REQUIRE(x && depth && type_tab && attr_tab && depth_tab && X, "embed: null pointer");
+  DAGNN_REQUIRE(N > 0 && N < (1ll << 31) && D > 0 && ldx >= D && max_depth >= 0, "embed: sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && ((((uintptr_t)type_tab | (uintptr_t)attr_tab | (uintptr_t)depth_tab | (uintptr_t)X) & 15) == 0);
+  const int blocks = (int)((N + 7) / 8 < 148 * 16 ? (N + 7) / 8 : 148 * 16);
+  if (vec) k_embed<true><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx);
+  else k_embed<false><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx);
+  return check_launch("k_embed");
+}
+
+extern "C" int dagnn_readout_f32(const DagnnSchedule* s, const DagnnReadoutBlock* blocks, int32_t nblocks, int32_t pool, float* out,
+                                 int64_t ldo, void* stream_) {
+  DAGNN_REQUIRE(s && blocks && out, "readout: null pointer");
+  DAGNN_REQUIRE(nblocks > 0 && nblocks <= DAGNN_MAX_READOUT_BLOCKS, "readout: nblocks");
+  DAGNN_REQUIRE(pool >= 0 && pool <= 2, "readout: pool");
+  DAGNN_REQUIRE(s->B > 0 && s->gptr, "readout: schedule has no graph pointers");
+  ReadoutArgs a;
+  a.nblocks = nblocks; a.pool = pool; a.B = (int)s->B;
+  a.gptr = s->gptr;
+  for (int d = 0; d < DAGNN_MAX_DIRS; ++d) a.pos[d] = d < s->dirs ? s->pos[d] : nullptr;
+  int maxw = 0;
+  for (int i = 0; i < nblocks; ++i) {
+    a.blk[i] = blocks[i];
+    DAGNN_REQUIRE(blocks[i].src && blocks[i].width > 0 && blocks[i].ld >= blocks[i].width, "readout: block");
+    DAGNN_REQUIRE(blocks[i].filter >= 0 && blocks[i].filter <= 3, "readout: filter");
+    DAGNN_REQUIRE(blocks[i].filter != 1 || blocks[i].filter_lvl, "readout: filter_lvl");
+    DAGNN_REQUIRE(!blocks[i].index_mode || (blocks[i].dir >= 0 && blocks[i].dir < s->dirs), "readout: dir");
+    maxw = blocks[i].width > maxw ? blocks[i].width : maxw;
+  }
+  dim3 grid((unsigned)s->B, (unsigned)nblocks, (unsigned)ceil_div(maxw, 128));
+  k_readout<<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(a, out, ldo);
+  return check_launch("k_readout");
+}

@@ -1,0 +1,106 @@
+// Parameter packing for one (direction, layer) — layout documented in include/dagnn_b200.h.
+// Runs once per parameter version (not per forward): transposes the GRU weights into the K-major,
+// zero-padded, unit-sliced stream the level kernel bulk-copies, and folds the attention linear layer into
+// a key vector + two edge-type coefficients.
+#include "common.cuh"
+
+namespace dagnn {
+
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                                      DagnnPackLayout L, float* __restrict__ packed) {
+  const int K = L.Kin + L.Kh;
+  const int64_t total = (int64_t)L.NS * K * 3 * DAGNN_UNIT_SLICE;
+  float* w = packed + L.w_off;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(idx % DAGNN_UNIT_SLICE);
+    const int g = (int)((idx / DAGNN_UNIT_SLICE) % 3);
+    const int k = (int)((idx / (3 * DAGNN_UNIT_SLICE)) % K);
+    const int sl = (int)(idx / ((int64_t)3 * DAGNN_UNIT_SLICE * K));
+    const int unit = sl * DAGNN_UNIT_SLICE + u;
+    float v = 0.f;
+    if (unit < L.H) {
+      if (k < L.Kin) {
+        if (k < L.Din) v = w_ih[((size_t)g * L.H + unit) * L.Din + k];
+      } else {
+        const int kh = k - L.Kin;
+        if (kh < L.H) v = w_hh[((size_t)g * L.H + unit) * L.H + kh];
+      }
+    }
+    w[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pack_small(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                    const float* __restrict__ attn_w, int Dq, const float* __restrict__ edge_w,
+                                                    DagnnPackLayout L, float* __restrict__ packed) {
+  const int HP = L.NS * DAGNN_UNIT_SLICE;
+  float* bias = packed + L.bias_off;
+  float* wk = packed + L.wk_off;
+  float* attnc = packed + L.attnc_off;
+  float* vidk = packed + L.vidk_off;
+  for (int u = threadIdx.x; u < HP; u += blockDim.x) {
+    const bool in = u < L.H;
+    bias[0 * HP + u] = in ? b_ih[u] + b_hh[u] : 0.f;
+    bias[1 * HP + u] = in ? b_ih[L.H + u] + b_hh[L.H + u] : 0.f;
+    bias[2 * HP + u] = in ? b_ih[2 * L.H + u] : 0.f;
+    bias[3 * HP + u] = in ? b_hh[2 * L.H + u] : 0.f;
+    wk[u] = in ? attn_w[Dq + u] : 0.f;
+  }
+  for (int j = threadIdx.x; j < L.nvid; j += blockDim.x) vidk[j] = attn_w[Dq + L.H + j];
+  // attnc[c] = sum_u wk[u] * W_e[u, c]
+  __shared__ float red[2][8];
+  float s0 = 0.f, s1 = 0.f;
+  if (edge_w) {
+    for (int u = threadIdx.x; u < L.H; u += blockDim.x) {
+      const float k = attn_w[Dq + u];
+      s0 += k * edge_w[2 * u];
+      s1 += k * edge_w[2 * u + 1];
+    }
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    attnc[0] = a; attnc[1] = b; attnc[2] = 0.f; attnc[3] = 0.f;
+  }
+}
+
+}  // namespace dagnn
+
+using namespace dagnn;
+
+extern "C" int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out) {
+  DAGNN_REQUIRE(out && Din > 0 && H > 0 && nvid >= 0, "pack_layout args");
+  DagnnPackLayout L;
+  L.Din = Din; L.H = H; L.nvid = nvid;
+  L.Kin = round_up(Din, DAGNN_K_BLOCK);
+  L.Kh = round_up(H, DAGNN_K_BLOCK);
+  L.NS = ceil_div(H, DAGNN_UNIT_SLICE);
+  const int64_t HP = (int64_t)L.NS * DAGNN_UNIT_SLICE;
+  int64_t off = 0;
+  L.w_off = off;     off += (int64_t)L.NS * (L.Kin + L.Kh) * 3 * DAGNN_UNIT_SLICE;
+  L.bias_off = off;  off += 4 * HP;
+  L.wk_off = off;    off += HP;
+  L.attnc_off = off; off += 4;
+  L.vidk_off = off;  off += round_up64(nvid, 4);
+  L.total_floats = off;
+  *out = L;
+  return DAGNN_OK;
+}
+
+extern "C" int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const float* bias_ih, const float* bias_hh,
+                                     const float* attn_w, int32_t Dq, const float* edge_w, const DagnnPackLayout* layout,
+                                     float* packed, void* stream_) {
+  DAGNN_REQUIRE(weight_ih && weight_hh && bias_ih && bias_hh && attn_w && layout && packed, "pack_params: null pointer");
+  DAGNN_REQUIRE(Dq >= 0, "pack_params: Dq");
+  DAGNN_REQUIRE((((uintptr_t)packed) & 15) == 0, "pack_params: packed must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int64_t total = (int64_t)layout->NS * (layout->Kin + layout->Kh) * 3 * DAGNN_UNIT_SLICE;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  k_pack_weights<<<blocks, 256, 0, st>>>(weight_ih, weight_hh, *layout, packed);
+  if (int rc = check_launch("k_pack_weights")) return rc;
+  k_pack_small<<<1, 256, 0, st>>>(bias_ih, bias_hh, attn_w, Dq, edge_w, *layout, packed);
+  return check_launch("k_pack_small");
+}

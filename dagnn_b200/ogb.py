@@ -1,0 +1,177 @@
+"""OGB flavour of DAGNN — drop-in for `ogbg-code/model/dagnn.py` (class DAGNN, :16-215) and the
+`ASTNodeEncoder` of `ogbg-code/utils.py:7-28`, with the level sweep running in libdagnn_sm100.so.
+
+Same constructor signature, same parameter names/shapes (checkpoints of the reference load with
+`load_state_dict`), same `forward(G)` contract: `G` carries `x int64[N,2]`, `node_depth int64[N,1]`,
+`edge_index int64[2,E]`, `edge_attr fp32[E,2]`, `batch int64[N]`, `_bi_layer_idx0/1`, `_bi_layer_index0/1`
+on the CUDA device; returns a list of `max_seq_len` tensors `[B, num_vocab]` (or `[B, num_class]`).
+
+Scope: the default aggregator `agg="attn_h"` with GRU cells (`recurr=1`), uni/bidirectional,
+`out_wx`, `out_pool_all`, `out_pool` in {max, mean, add}. Other aggregators / `agg_x` / `recurr=0` /
+`out_pool="attn"` raise NotImplementedError at construction (§8f row 4), they never fall back to eager torch.
+Forward only: calling it with autograd enabled on trainable parameters raises (backward = §8f row 1).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import runtime as rt
+
+NA_ATTN_H = "attn_h"
+P_MAX, P_MEAN, P_ADD, P_ATTN = "max", "mean", "add", "attn"
+
+
+class ASTNodeEncoder(nn.Module):
+    """ogbg-code/utils.py:7-28 — three embedding tables summed; the gather-sum runs in `dagnn_embed_f32`."""
+
+    def __init__(self, emb_dim, num_nodetypes, num_nodeattributes, max_depth):
+        super().__init__()
+        self.max_depth = max_depth
+        self.type_encoder = nn.Embedding(num_nodetypes, emb_dim)
+        self.attribute_encoder = nn.Embedding(num_nodeattributes, emb_dim)
+        self.depth_encoder = nn.Embedding(self.max_depth + 1, emb_dim)
+
+    def forward(self, x, depth):
+        return rt.embed(x, depth, self.type_encoder.weight, self.attribute_encoder.weight, self.depth_encoder.weight,
+                        self.max_depth)
+
+
+class AttnConv(nn.Module):
+    """Parameter container with the names of the reference's AttnConv (dagnn.py:347-359). The message
+    passing itself is fused into the level kernel."""
+
+    def __init__(self, attn_q_dim, emb_dim, attn_dim=0, num_relations=1, reverse=False):
+        super().__init__()
+        assert attn_q_dim > 0 and emb_dim > 0
+        attn_dim = attn_dim if attn_dim > 0 else emb_dim
+        self.reverse = reverse
+        self.wea = num_relations > 1
+        if self.wea:
+            self.edge_encoder = nn.Linear(num_relations, attn_dim)
+        self.attn_lin = nn.Linear(attn_q_dim + attn_dim, 1)
+
+
+def _forward_only_guard(module: nn.Module):
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise RuntimeError("dagnn_b200 implements the forward pass only (backward is SURVEY.md §8f row 1): call the "
+                           "module under torch.no_grad() / torch.inference_mode(). There is no autograd fallback.")
+
+
+class DAGNN(nn.Module):
+
+    def __init__(self, num_vocab, max_seq_len, emb_dim, hidden_dim, out_dim,
+                 num_rels=2, w_edge_attr=True, num_layers=2, bidirectional=True, mapper_bias=True,
+                 agg_x=False, agg=NA_ATTN_H, out_wx=True, out_pool_all=True, out_pool=P_MAX, encoder=None, dropout=0.0,
+                 word_vectors=None, emb_dims=[], activation=None, num_class=0, recurr=1):
+        super().__init__()
+        self.num_class = num_class
+        self.num_vocab = num_vocab
+        self.max_seq_len = max_seq_len
+        if agg_x and hidden_dim < emb_dim:
+            raise ValueError('Hidden dimension too small for input.')     # dagnn.py:27-28
+        if agg != NA_ATTN_H or agg_x or not recurr:
+            raise NotImplementedError("dagnn_b200 covers agg='attn_h', agg_x=False, recurr=1 (SURVEY.md §8f row 4); "
+                                      "got agg=%r agg_x=%r recurr=%r" % (agg, agg_x, recurr))
+        if out_pool not in (P_MAX, P_MEAN, P_ADD):
+            raise NotImplementedError("out_pool=%r is not covered (max / mean / add are)" % (out_pool,))
+        if encoder is None:
+            raise NotImplementedError("pass encoder=ASTNodeEncoder(...) (main_pyg.py:248,396-401); EmbeddingBag "
+                                      "encoders (init_encoder, dagnn.py:218-223) are not covered")
+        self.agg_x, self.agg_attn, self.agg_attn_x = False, True, False
+        self.bidirectional = bidirectional
+        self.dirs = [0, 1] if bidirectional else [0]
+        self.num_layers = num_layers
+        self.out_wx = out_wx
+        self.output_all = out_pool_all
+        self.out_pool = out_pool
+        self.recurr = recurr
+        self.emb_dim = emb_dim
+        self.hidden_dim = hidden_dim
+        nd = len(self.dirs)
+        self.out_hidden_dim = emb_dim * nd + hidden_dim * nd * num_layers if out_wx else hidden_dim * nd * num_layers
+        self.encoder = encoder
+        self.w_edge_attr = bool(w_edge_attr)
+        num_rels = num_rels if w_edge_attr else 1
+        if num_rels not in (1, 2):
+            raise NotImplementedError("edge_attr must have 2 columns (utils2.py:45,68)")
+        # both aggregator lists exist even when unidirectional, like the reference (dagnn.py:64-67)
+        self.node_aggr_0 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
+                                                   attn_dim=hidden_dim) for l in range(num_layers)])
+        self.node_aggr_1 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
+                                                   attn_dim=hidden_dim, reverse=True) for l in range(num_layers)])
+        for i in self.dirs:
+            setattr(self, "cells_{}".format(i), nn.ModuleList(
+                [nn.GRUCell(emb_dim if l == 0 else hidden_dim, hidden_dim) for l in range(num_layers)]))
+        self.dropout = nn.Dropout(dropout)
+        if self.num_class > 0:
+            self.graph_pred_linear = nn.Linear(self.out_hidden_dim, self.num_class)
+        else:
+            self.graph_pred_linear_list = nn.ModuleList()
+            if self.num_vocab == 1:
+                self.graph_pred_linear_list.append(nn.Sequential(nn.Linear(self.out_hidden_dim, self.num_vocab), nn.ReLU()))
+            else:
+                for _ in range(max_seq_len):
+                    self.graph_pred_linear_list.append(nn.Linear(self.out_hidden_dim, self.num_vocab))
+        self._packed = rt.PackedParams()
+
+    # ------------------------------------------------------------------ pieces of forward
+    def _num_graphs(self, G) -> int:
+        ng = getattr(G, "num_graphs", None)
+        return int(ng) if ng is not None else int(G.batch[-1].item()) + 1
+
+    def build_schedule(self, G) -> rt.Schedule:
+        lv = [G._bi_layer_idx0, G._bi_layer_idx1][:len(self.dirs)]
+        ids = [G._bi_layer_index0, G._bi_layer_index1][:len(self.dirs)]
+        ea = G.edge_attr if self.w_edge_attr else None
+        return rt.Schedule.build(G.edge_index, lv, ids, ea, G.batch, self._num_graphs(G))
+
+    def _pack(self, device) -> rt.PackedParams:
+        cells = [getattr(self, "cells_%d" % d) for d in self.dirs]
+        aggrs = [getattr(self, "node_aggr_%d" % d) for d in self.dirs]
+        return self._packed.update(cells, aggrs, self.emb_dim, self.hidden_dim, 0, self.w_edge_attr, device)
+
+    def node_states(self, G, sched=None):
+        """encoder + level sweep: returns (X [N,D], Hs [dirs, layers, N, ldh] in position order, schedule)."""
+        X = self.encoder(G.x, G.node_depth.view(-1, ))
+        if X.shape[1] != self.emb_dim:
+            raise ValueError("encoder produced width %d, emb_dim is %d" % (X.shape[1], self.emb_dim))
+        sched = sched if sched is not None else self.build_schedule(G)
+        packed = self._pack(X.device)
+        Hs = rt.sweep(sched, X, packed, self.emb_dim, self.hidden_dim, self.num_layers, 0, self.w_edge_attr)
+        return X, Hs, sched
+
+    def readout(self, G, X, Hs, sched) -> torch.Tensor:
+        """dagnn.py:184-202."""
+        H, Lr, blocks = self.hidden_dim, self.num_layers, []
+        lvl = [G._bi_layer_idx0, G._bi_layer_idx1]
+        col = 0
+        if self.bidirectional and not self.output_all:
+            for d in (0, 1):
+                filt = dict(filter=rt.FILTER_LVL0, filter_lvl=lvl[1 - d])   # d=0: sinks, d=1: sources (:119-126)
+                if self.out_wx:
+                    blocks.append(dict(src=X, width=self.emb_dim, index_mode=0, out_col=col, **filt)); col += self.emb_dim
+                for l in range(Lr):
+                    blocks.append(dict(src=Hs[d, l], width=H, index_mode=1, dir=d, out_col=col, **filt)); col += H
+        else:
+            filt = dict(filter=rt.FILTER_ALL) if self.output_all else dict(filter=rt.FILTER_LVL0, filter_lvl=lvl[1])
+            if self.out_wx:
+                blocks.append(dict(src=X, width=self.emb_dim, index_mode=0, out_col=col, **filt)); col += self.emb_dim
+            for d in self.dirs:
+                for l in range(Lr):
+                    blocks.append(dict(src=Hs[d, l], width=H, index_mode=1, dir=d, out_col=col, **filt)); col += H
+        return rt.readout(sched, blocks, self.out_pool, col, X.device)
+
+    def forward_readout(self, G):
+        """The north-star hot path: encoder -> schedule -> level sweeps (both directions) -> pooled readout."""
+        X, Hs, sched = self.node_states(G)
+        return self.readout(G, X, Hs, sched)
+
+    def forward(self, G):
+        _forward_only_guard(self)
+        out = self.forward_readout(G)
+        out = self.dropout(out)
+        if self.num_class > 0:
+            return self.graph_pred_linear(out)
+        return [self.graph_pred_linear_list[i](out) for i in range(self.max_seq_len)]

@@ -1,0 +1,263 @@
+"""Host-side plumbing between torch tensors and the C ABI (include/dagnn_b200.h).
+
+PyTorch is used here for device memory, the current stream and nothing else: every array is allocated as a
+torch tensor and handed to libdagnn_sm100.so as a raw pointer. No arithmetic of the path happens in torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DagnnPackLayout, DagnnReadoutBlock, DagnnSchedule, DagnnSweepArgs, check, lib)
+
+POOLS = {"max": 0, "mean": 1, "add": 2}
+FILTER_ALL, FILTER_LVL0, FILTER_LAST, FILTER_FIRST = 0, 1, 2, 3
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise _lib.DagnnError("%s must live on a CUDA device (dagnn_b200 has no CPU path); got %s" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.DagnnError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, max_depth: int) -> torch.Tensor:
+    """ASTNodeEncoder.forward (ogbg-code/utils.py:26-28) -> fp32 [N, D]."""
+    x = _req_cuda(x, "x", torch.int64)
+    depth = _req_cuda(depth.view(-1), "node_depth", torch.int64)
+    T, A, P = (_req_cuda(t.detach(), "embedding table", torch.float32) for t in (type_tab, attr_tab, depth_tab))
+    N, D = x.shape[0], T.shape[1]
+    X = torch.empty(N, D, device=x.device, dtype=torch.float32)
+    check(lib().dagnn_embed_f32(_ptr(x), _ptr(depth), _ptr(T), _ptr(A), _ptr(P), int(max_depth), N, D, _ptr(X), D,
+                                _stream()), "dagnn_embed_f32")
+    return X
+
+
+class Schedule(object):
+    """Level-sorted node order + in-edge CSR per direction, built on the device (schedule.cu)."""
+
+    def __init__(self):
+        self.c = DagnnSchedule()
+        self.buf = None
+        self.host_head = None
+        self.lvl_off_host: List[np.ndarray] = []
+        self.num_levels: List[int] = []
+        self._keep = []
+
+    @staticmethod
+    def build(edge_index: torch.Tensor, levels: Sequence[torch.Tensor], node_ids: Sequence[Optional[torch.Tensor]],
+              edge_attr: Optional[torch.Tensor], batch: Optional[torch.Tensor], num_graphs: int,
+              max_levels: int = 256) -> "Schedule":
+        dirs = len(levels)
+        dev = edge_index.device
+        edge_index = _req_cuda(edge_index, "edge_index", torch.int64)
+        levels = [_req_cuda(l, "level array", torch.int64) for l in levels]
+        node_ids = [None if n is None else _req_cuda(n, "node id array", torch.int64) for n in node_ids]
+        if edge_attr is not None:
+            edge_attr = _req_cuda(edge_attr, "edge_attr", torch.float32)
+            if edge_attr.dim() != 2 or edge_attr.shape[1] != 2:
+                raise _lib.DagnnError("edge_attr must be [E, 2] (ogbg-code/utils2.py:45,68)")
+        if batch is not None:
+            batch = _req_cuda(batch, "batch", torch.int64)
+        N, E, B = int(levels[0].shape[0]), int(edge_index.shape[1]), int(num_graphs)
+        while True:
+            s = Schedule()
+            ML = int(max_levels)
+            head = 8 + dirs * (ML + 1)
+            sizes = [("head", head)]
+            for d in range(dirs):
+                sizes += [("perm%d" % d, N), ("pos%d" % d, N), ("rowptr%d" % d, N + 1), ("col%d" % d, E), ("eid%d" % d, E)]
+                if edge_attr is not None:
+                    sizes.append(("eattr%d" % d, 2 * E))
+            sizes.append(("gptr", B + 1))
+            offs, tot = {}, 0
+            for k, n in sizes:
+                offs[k] = tot
+                tot += _align(max(n, 1))
+            ws_bytes = lib().dagnn_schedule_workspace_bytes(N, E, ML)
+            buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
+            s.buf = buf
+            view = lambda k, n: buf[offs[k]: offs[k] + n]
+            c = s.c
+            c.N, c.E, c.B, c.dirs, c.max_levels = N, E, B, dirs, ML
+            s.summary = view("head", 8)
+            c.summary = s.summary.data_ptr()
+            s.perm, s.pos, s.lvl_off, s.rowptr, s.col, s.eid, s.eattr = [], [], [], [], [], [], []
+            for d in range(dirs):
+                s.perm.append(view("perm%d" % d, N)); s.pos.append(view("pos%d" % d, N))
+                s.lvl_off.append(buf[offs["head"] + 8 + d * (ML + 1): offs["head"] + 8 + (d + 1) * (ML + 1)])
+                s.rowptr.append(view("rowptr%d" % d, N + 1)); s.col.append(view("col%d" % d, E)); s.eid.append(view("eid%d" % d, E))
+                s.eattr.append(view("eattr%d" % d, 2 * E).view(torch.float32).view(E, 2) if edge_attr is not None else None)
+                c.perm[d], c.pos[d], c.lvl_off[d] = s.perm[d].data_ptr(), s.pos[d].data_ptr(), s.lvl_off[d].data_ptr()
+                c.rowptr[d], c.col[d], c.eid[d] = s.rowptr[d].data_ptr(), s.col[d].data_ptr(), s.eid[d].data_ptr()
+                c.eattr[d] = s.eattr[d].data_ptr() if edge_attr is not None else None
+            s.gptr = view("gptr", B + 1)
+            c.gptr = s.gptr.data_ptr()
+            ws = buf[tot:]
+            check(lib().dagnn_schedule_build(_ptr(edge_index), _ptr(levels[0]), _ptr(levels[1]) if dirs == 2 else None,
+                                             _ptr(node_ids[0]), _ptr(node_ids[1]) if dirs == 2 else None,
+                                             _ptr(edge_attr), _ptr(batch), C.byref(c), ws.data_ptr(), ws_bytes, _stream()),
+                  "dagnn_schedule_build")
+            # the one host<->device round trip of a forward: 8 + dirs*(ML+1) ints (the reference syncs at
+            # dagnn.py:137 and once per node at :155)
+            host = torch.empty(head, dtype=torch.int32, pin_memory=True)
+            host.copy_(buf[:head], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            hn = host.numpy()
+            status = int(hn[2])
+            if status == 1 and ML < (1 << 22):
+                max_levels = ML * 8
+                continue
+            if status != 0:
+                raise _lib.DagnnError("schedule build: status %d (1: level >= max_levels, 2: node id / edge endpoint / "
+                                      "batch vector out of range)" % status)
+            s.host_head = host
+            s.num_levels = [int(hn[d]) for d in range(dirs)]
+            s.lvl_off_host = [hn[8 + d * (ML + 1): 8 + (d + 1) * (ML + 1)] for d in range(dirs)]
+            s._keep = [edge_index, levels, node_ids, edge_attr, batch]
+            s.has_edge_attr = edge_attr is not None
+            return s
+
+    # ---- views used by tests (bit-exact parity of the integer pre-pass) ----
+    def level_nodes(self, d: int, l: int) -> torch.Tensor:
+        a, b = int(self.lvl_off_host[d][l]), int(self.lvl_off_host[d][l + 1])
+        return self.perm[d][a:b].long()
+
+    def level_edges(self, d: int, l: int) -> torch.Tensor:
+        a, b = int(self.lvl_off_host[d][l]), int(self.lvl_off_host[d][l + 1])
+        rp = self.rowptr[d]
+        e0, e1 = int(rp[a]), int(rp[b])
+        return self.eid[d][e0:e1].long()
+
+
+class PackedParams(object):
+    """Packed GRU + attention parameters of every (direction, layer); re-packed when a parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.blobs: List[List[torch.Tensor]] = []
+        self.layouts: List[DagnnPackLayout] = []
+
+    @staticmethod
+    def layout(Din: int, H: int, nvid: int) -> DagnnPackLayout:
+        L = DagnnPackLayout()
+        check(lib().dagnn_pack_layout(Din, H, nvid, C.byref(L)), "dagnn_pack_layout")
+        return L
+
+    def update(self, cells, aggrs, Din: int, H: int, nvid: int, use_edge_attr: bool, device):
+        """cells[d][i]: nn.GRUCell; aggrs[d][i]: module with .attn_lin (and .edge_encoder when use_edge_attr)."""
+        params = []
+        for d in range(len(cells)):
+            for i in range(len(cells[d])):
+                cell, ag = cells[d][i], aggrs[d][i]
+                params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag.attn_lin.weight]
+                if use_edge_attr:
+                    params.append(ag.edge_encoder.weight)
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (Din, H, nvid, use_edge_attr)
+        if key == self.key:
+            return self
+        self.blobs, self.layouts = [], []
+        for d in range(len(cells)):
+            row = []
+            for i in range(len(cells[d])):
+                cell, ag = cells[d][i], aggrs[d][i]
+                din = Din if i == 0 else H
+                L = self.layout(din, H, nvid)
+                for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag.attn_lin.weight):
+                    _req_cuda(p, "parameter", torch.float32)
+                aw = ag.attn_lin.weight.detach().contiguous()
+                Dq = aw.shape[1] - H - nvid
+                if Dq < 0:
+                    raise _lib.DagnnError("attn_lin.weight has %d columns < H + nvid" % aw.shape[1])
+                ew = ag.edge_encoder.weight.detach().contiguous() if use_edge_attr else None
+                if ew is not None and tuple(ew.shape) != (H, 2):
+                    raise _lib.DagnnError("edge_encoder.weight must be [H, 2]")
+                blob = torch.empty(int(L.total_floats), device=device, dtype=torch.float32)
+                check(lib().dagnn_pack_params_f32(_ptr(cell.weight_ih.detach().contiguous()), _ptr(cell.weight_hh.detach().contiguous()),
+                                                  _ptr(cell.bias_ih.detach().contiguous()), _ptr(cell.bias_hh.detach().contiguous()),
+                                                  _ptr(aw), int(Dq), _ptr(ew), C.byref(L), _ptr(blob), _stream()),
+                      "dagnn_pack_params_f32")
+                row.append(blob)
+                if d == 0:
+                    self.layouts.append(L)
+            self.blobs.append(row)
+        self.key = key
+        return self
+
+
+def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: int, num_layers: int, nvid: int = 0,
+          use_edge_attr: bool = False) -> torch.Tensor:
+    """The level sweep. Returns Hs fp32 [dirs, layers, N, ldh] in POSITION order (row p = node perm[d][p])."""
+    X = _req_cuda(X, "X", torch.float32)
+    dirs, N = sched.c.dirs, sched.c.N
+    if sched.num_levels[0] < 1:
+        raise _lib.DagnnError("empty batch")
+    if dirs == 2 and sched.num_levels[1] > sched.num_levels[0]:
+        raise _lib.DagnnError("direction 1 has more levels (%d) than direction 0 (%d): level arrays are not the "
+                              "longest-path levels of one DAG" % (sched.num_levels[1], sched.num_levels[0]))
+    ldh = (H + 3) // 4 * 4
+    Hs = torch.empty(dirs, num_layers, N, ldh, device=X.device, dtype=torch.float32)
+    a = DagnnSweepArgs()
+    a.sched = C.pointer(sched.c)
+    for d in range(dirs):
+        a.lvl_off_host[d] = sched.lvl_off_host[d].ctypes.data_as(C.POINTER(C.c_int32))
+        for i in range(num_layers):
+            a.Hs[d][i] = Hs[d, i].data_ptr()
+            a.packed[d][i] = packed.blobs[d][i].data_ptr()
+    a.num_levels, a.num_layers = sched.num_levels[0], num_layers
+    a.Din, a.H, a.nvid = Din, H, nvid
+    a.X, a.ldx, a.ldh = X.data_ptr(), X.stride(0), ldh
+    a.use_edge_attr = 1 if use_edge_attr else 0
+    check(lib().dagnn_sweep_forward_f32(C.byref(a), _stream()), "dagnn_sweep_forward_f32")
+    return Hs
+
+
+def readout(sched: Schedule, blocks: Sequence[dict], pool: str, out_width: int, device) -> torch.Tensor:
+    """blocks: dicts with src (2-D fp32 tensor), width, index_mode, dir, filter, filter_lvl, out_col."""
+    arr = (DagnnReadoutBlock * len(blocks))()
+    keep = []
+    for k, b in enumerate(blocks):
+        src = b["src"]
+        arr[k].src, arr[k].ld, arr[k].width = src.data_ptr(), src.stride(0), int(b["width"])
+        arr[k].index_mode, arr[k].dir, arr[k].filter = int(b.get("index_mode", 0)), int(b.get("dir", 0)), int(b.get("filter", 0))
+        fl = b.get("filter_lvl")
+        if fl is not None:
+            fl = _req_cuda(fl, "filter_lvl", torch.int64)
+            keep.append(fl)
+        arr[k].filter_lvl = _ptr(fl)
+        arr[k].out_col = int(b["out_col"])
+    out = torch.empty(sched.c.B, out_width, device=device, dtype=torch.float32)
+    check(lib().dagnn_readout_f32(C.byref(sched.c), arr, len(blocks), POOLS[pool], out.data_ptr(), out.stride(0), _stream()),
+          "dagnn_readout_f32")
+    return out
+
+
+def states_to_node_order(sched: Schedule, Hs: torch.Tensor, H: int) -> List[List[torch.Tensor]]:
+    """Hs [dirs, layers, N, ldh] (position order) -> G.h-style nested list of [N, H] tensors in node order."""
+    out = []
+    for d in range(Hs.shape[0]):
+        row = []
+        for i in range(Hs.shape[1]):
+            dst = torch.empty(Hs.shape[2], H, device=Hs.device, dtype=torch.float32)
+            check(lib().dagnn_states_to_node_order_f32(C.byref(sched.c), d, Hs[d, i].data_ptr(), Hs.stride(2), H, dst.data_ptr(),
+                                                       H, _stream()), "dagnn_states_to_node_order_f32")
+            row.append(dst)
+        out.append(row)
+    return out

@@ -1,0 +1,178 @@
+/*
+ * dagnn_b200.h — C ABI of libdagnn_sm100.so: the DAGNN layer-wise (topological-level) forward on B200.
+ *
+ * The reference (vthost/DAGNN @ b065cd5) has NO FFI / plugin ABI for this path: its boundary is the Python
+ * nn.Module API. This header is the drop-in boundary a maintainer would bind instead of the
+ * library calls listed in SURVEY.md §2.1 (K1-K13); each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers + sizes + leading dimensions; no torch / C++ types cross the boundary;
+ *   - the caller owns every buffer (nothing is allocated inside; scratch comes in through *workspace*
+ *     arguments sized by the matching *_bytes() query);
+ *   - every call is asynchronous on the given CUDA stream (cudaStream_t passed as void*), no hidden sync;
+ *   - return value: 0 on success, negative DAGNN_E_* otherwise; dagnn_last_error() gives a thread-local
+ *     message. Nothing throws across the ABI;
+ *   - no global mutable state except per-process cached function attributes and a launch counter;
+ *     safe to call from several host threads on different streams / devices.
+ *   - fp32 everywhere ("f32" suffix); integer schedule arrays are int32 on the device (inputs int64 as PyG
+ *     provides them).
+ */
+#ifndef DAGNN_B200_H_
+#define DAGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAGNN_ABI_VERSION 1
+#define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
+#define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
+#define DAGNN_UNIT_SLICE 128        /* hidden units per weight slice of the packed layout        */
+#define DAGNN_K_BLOCK 16            /* K granularity of the packed layout (rows per stage)       */
+#define DAGNN_MAX_READOUT_BLOCKS 20 /* column blocks of one readout call                         */
+
+enum {
+  DAGNN_OK = 0,
+  DAGNN_E_INVALID = -1,   /* bad argument (null pointer, size, alignment)                    */
+  DAGNN_E_CUDA = -2,      /* a CUDA runtime call / launch failed                             */
+  DAGNN_E_WORKSPACE = -3, /* workspace too small                                             */
+  DAGNN_E_UNSUPPORTED = -4
+};
+
+int dagnn_abi_version(void);
+const char* dagnn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+int64_t dagnn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Node encoder:  X[v,:] = T[x[v,0],:] + A[x[v,1],:] + P[min(depth[v], max_depth),:]
+ * replaces ASTNodeEncoder.forward, ogbg-code/utils.py:26-28 (called at ogbg-code/model/dagnn.py:139).
+ * x int64 [N,2] row-major, depth int64 [N]; tables fp32 row-major with leading dimension D; X fp32 [N, ldx].
+ * Unlike the reference it does not clamp `depth` in place.
+ * --------------------------------------------------------------------------------------------------------- */
+int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
+                    const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Integer pre-pass (bit-exact): level-sorted node order + in-edge CSR per direction.
+ * replaces the per-level boolean-mask selects and the per-node O(E) edge scans of
+ * ogbg-code/model/dagnn.py:130-137,146-147,151-157 (dvae/dagnn.py:104,111-112,116-122).
+ *
+ * For direction d, "position" p enumerates nodes sorted by (level_d, index in the level array) — i.e.
+ * positions [lvl_off[d][l], lvl_off[d][l+1]) are exactly the reference's `layer` list of level l, in its order.
+ * Row p of the CSR lists the edges e with edge_index[1-d][e] == perm[d][p] in ascending e (the reference's
+ * `le_idx` order); col = position (in direction d's order) of the neighbour edge_index[d][e].
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct DagnnSchedule {
+  int64_t N, E, B;
+  int32_t dirs;        /* 1 or 2                                                              */
+  int32_t max_levels;  /* capacity of lvl_off (entries: max_levels + 1)                        */
+  int32_t* perm[DAGNN_MAX_DIRS];    /* [N]   position -> node id                               */
+  int32_t* pos[DAGNN_MAX_DIRS];     /* [N]   node id  -> position                              */
+  int32_t* lvl_off[DAGNN_MAX_DIRS]; /* [max_levels+1] first position of each level; [L] = N    */
+  int32_t* rowptr[DAGNN_MAX_DIRS];  /* [N+1] CSR row pointers, rows indexed by position        */
+  int32_t* col[DAGNN_MAX_DIRS];     /* [E]   neighbour position                                */
+  int32_t* eid[DAGNN_MAX_DIRS];     /* [E]   original edge id (ascending inside a row)         */
+  float* eattr[DAGNN_MAX_DIRS];     /* [E,2] edge_attr rows in CSR order, or NULL              */
+  int32_t* gptr;                    /* [B+1] first node id of each graph (batch vector sorted) */
+  /* summary[0]=num_levels of dir 0, [1]=num_levels of dir 1, [2]=status (0 ok, 1 level >= max_levels,
+   * 2 node id / edge endpoint out of range), [3..7] reserved.                                       */
+  int32_t* summary;                 /* [8]                                                     */
+} DagnnSchedule;
+
+size_t dagnn_schedule_workspace_bytes(int64_t N, int64_t E, int32_t max_levels);
+
+/* edge_index int64 [2,E]; lvl{0,1} int64 [N] levels; nid{0,1} int64 [N] node id of each level-array entry
+ * (NULL = identity; the reference's _bi_layer_index{0,1}); edge_attr fp32 [E,2] or NULL; batch int64 [N]
+ * (sorted, PyG convention) or NULL when B == 0. All output arrays of *sched must be allocated by the caller. */
+int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const int64_t* lvl1,
+                         const int64_t* nid0, const int64_t* nid1, const float* edge_attr, const int64_t* batch,
+                         const DagnnSchedule* sched, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Parameter packing for one (direction, layer): GRU weights -> K-major, zero-padded, unit-sliced stream
+ * that the level kernel bulk-copies into shared memory; attention vector -> key part + edge-type coefficients.
+ * Sources: nn.GRUCell weight_ih [3H,Din], weight_hh [3H,H], bias_ih/bias_hh [3H]   (dagnn.py:79-81),
+ *          attn_lin.weight [1, Dq + H (+nvid)] (dagnn.py:359; dvae/dagnn.py:47-48,357),
+ *          edge_encoder.weight [H,2] (dagnn.py:356) or NULL.
+ * The query part of attn_lin (first Dq columns), attn_lin.bias and edge_encoder.bias add the same constant
+ * to every in-edge score of a node and cancel in the softmax, so they are not packed.
+ * Layout of `packed` (floats), all offsets from dagnn_pack_layout():
+ *   w     [NS][Kin+Kh][3][128]  NS=ceil(H/128); Kin=roundup(Din,16); Kh=roundup(H,16)
+ *   bias  [4][NS*128]           b_r=b_ir+b_hr, b_z=b_iz+b_hz, b_in, b_hn
+ *   wk    [NS*128]              key weights on the hidden state
+ *   attnc [4]                   {wk·W_e[:,0], wk·W_e[:,1], 0, 0}
+ *   vidk  [nvid]                key weights on the one-hot vertex id (D-VAE NA), nvid may be 0
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct DagnnPackLayout {
+  int32_t Din, H, Kin, Kh, NS, nvid;
+  int64_t w_off, bias_off, wk_off, attnc_off, vidk_off, total_floats;
+} DagnnPackLayout;
+
+int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out);
+
+int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const float* bias_ih,
+                          const float* bias_hh, const float* attn_w, int32_t Dq, const float* edge_w,
+                          const DagnnPackLayout* layout, float* packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The level sweep (the hot path): for every direction d, level l (sequential) and stacked layer i,
+ *   m_v   = sum_e softmax_e( wk·h_e + wk·W_e a_e [+ vidk[nbr mod nvid]] ) * h_e     over ALL in-edges e of v,
+ *           h_e = H[d][i][nbr(e)] if level_d[nbr(e)] < l else 0      (level 0: m_v = 0, edges ignored)
+ *   inp_v = GRUCell_{d,i}(inp_v, m_v);  H[d][i][v] = inp_v          (inp_v starts as X[v])
+ * replaces dagnn.py:144-182 incl. AttnConv (:362-373), PyG propagate/softmax/scatter-add, nn.GRUCell (:181) and
+ * the index_put at :182; D-VAE variants dvae/dagnn.py:109-145, dvae/dagnn_bn.py:108-136.
+ * One fused kernel launch per wavefront step s = level + layer (all (d, layer) pairs of the step in one
+ * grid). States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
+ * `lvl_off_host[d]` is a host copy of sched->lvl_off[d][0..num_levels] (the launcher sizes grids from it).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct DagnnSweepArgs {
+  const DagnnSchedule* sched;
+  const int32_t* lvl_off_host[DAGNN_MAX_DIRS];
+  int32_t num_levels;                  /* levels swept (reference: max level of direction 0, + 1)  */
+  int32_t num_layers;
+  int32_t Din, H, nvid;                /* input width, hidden width, #vertex-id columns (0 = none) */
+  const float* X;                      /* [N, ldx] node features in NODE order                      */
+  int64_t ldx;
+  float* Hs[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];               /* [N, ldh] each, position order      */
+  int64_t ldh;                         /* >= roundup(H,4), multiple of 4                            */
+  const float* packed[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];     /* dagnn_pack_params_f32 outputs       */
+  int32_t use_edge_attr;               /* 1: add the edge-type score term (sched->eattr must exist) */
+} DagnnSweepArgs;
+
+int dagnn_sweep_forward_f32(const DagnnSweepArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Readout: out[g, out_col + c] = pool over selected nodes v of graph g of src[row(v), c]
+ * replaces dagnn.py:119-126,184-202 (cat over layers + mask/gather of output nodes + global_{max,mean,add}_pool)
+ * and the last/first-node gathers of dvae/dagnn.py:147-161, dvae/dagnn_bn.py:138-152.
+ *   row(v)  = v (index_mode 0, node order) or sched->pos[dir][v] (index_mode 1, position order)
+ *   filter  : 0 all nodes, 1 nodes with filter_lvl[v] == 0, 2 last node of the graph, 3 first node
+ *   pool    : 0 max, 1 mean, 2 add      (empty selection -> 0, like torch_scatter)
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct DagnnReadoutBlock {
+  const float* src;
+  int64_t ld;
+  int32_t width;
+  int32_t index_mode;
+  int32_t dir;
+  int32_t filter;
+  const int64_t* filter_lvl;
+  int32_t out_col;
+  int32_t reserved;
+} DagnnReadoutBlock;
+
+int dagnn_readout_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* blocks, int32_t nblocks, int32_t pool,
+                      float* out, int64_t ldo, void* stream);
+
+/* Un-permute states for inspection / tests: dst[v,:] = src[pos[dir][v],:]  (fp32 [N,H]) */
+int dagnn_states_to_node_order_f32(const DagnnSchedule* sched, int32_t dir, const float* src, int64_t lds,
+                                   int32_t H, float* dst, int64_t ldd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAGNN_B200_H_ */
