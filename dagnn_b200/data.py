@@ -350,3 +350,59 @@ def deterministic_init_(module: torch.nn.Module, seed: int) -> torch.nn.Module:
         with torch.no_grad():
             p.copy_(torch.from_numpy(np.asarray(v, dtype=np.float32)))
     return module
+
+
+# --------------------------------------------------------------------------------------
+# graph-level slicing of a batch (multi-GPU sharding, tests)
+# --------------------------------------------------------------------------------------
+def graph_node_counts(B: DagBatch) -> np.ndarray:
+    ng = int(getattr(B, "num_graphs", int(B.batch.max()) + 1))
+    return np.bincount(B.batch.numpy(), minlength=ng)
+
+
+def select_graphs(B: DagBatch, graph_ids) -> DagBatch:
+    """New batch made of the graphs `graph_ids` of B (in that order), node ids renumbered — the same result as
+    collating those graphs from scratch. Works for OGB-style (`_bi_layer_idx*`) and D-VAE-style (`bi_layer_index`)
+    batches. Host-side numpy; not on the hot path."""
+    graph_ids = np.asarray(list(graph_ids), dtype=np.int64)
+    batch = B.batch.numpy()
+    cnt = graph_node_counts(B)
+    first = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    new_first = np.concatenate([[0], np.cumsum(cnt[graph_ids])])[:-1]
+    nodes = np.concatenate([np.arange(first[g], first[g] + cnt[g]) for g in graph_ids]) if len(graph_ids) else np.zeros(0, np.int64)
+    new_id = np.full(len(batch), -1, dtype=np.int64)
+    new_id[nodes] = np.arange(len(nodes))
+    ei = B.edge_index.numpy()
+    # edges grouped by graph in the order of graph_ids, original order inside a graph
+    eg = batch[ei[0]] if ei.shape[1] else np.zeros(0, np.int64)
+    rank = np.full(len(cnt), -1, dtype=np.int64)
+    rank[graph_ids] = np.arange(len(graph_ids))
+    keep = np.nonzero(rank[eg] >= 0)[0] if ei.shape[1] else np.zeros(0, np.int64)
+    keep = keep[np.argsort(rank[eg[keep]], kind="stable")]
+    nodes_t, keep_t = torch.from_numpy(nodes), torch.from_numpy(keep)
+    out = DagBatch(num_graphs=len(graph_ids))
+    out.batch = torch.from_numpy(np.repeat(np.arange(len(graph_ids)), cnt[graph_ids]))
+    out.edge_index = torch.from_numpy(new_id[ei[:, keep]]).contiguous() if ei.shape[1] else B.edge_index.clone()
+    out.x = B.x[nodes_t]
+    if getattr(B, "edge_attr", None) is not None:
+        out.edge_attr = B.edge_attr[keep_t]
+    if hasattr(B, "node_depth"):
+        out.node_depth = B.node_depth[nodes_t]
+    if hasattr(B, "_bi_layer_idx0"):
+        ids = torch.arange(len(nodes), dtype=torch.long)
+        out._bi_layer_idx0, out._bi_layer_idx1 = B._bi_layer_idx0[nodes_t], B._bi_layer_idx1[nodes_t]
+        out._bi_layer_index0, out._bi_layer_index1 = ids, ids.clone()
+    if hasattr(B, "bi_layer_index"):
+        bi = B.bi_layer_index[:, :, nodes_t].clone()
+        bi[:, 1] = torch.arange(len(nodes), dtype=torch.long)
+        out.bi_layer_index = bi.contiguous()
+    return out
+
+
+def split_batch(B: DagBatch, ranges) -> List[DagBatch]:
+    return [select_graphs(B, r) for r in ranges]
+
+
+def shard_batch(B: DagBatch, world_size: int) -> List[DagBatch]:
+    """Node-balanced contiguous graph shards, one per rank (rule of ogbg-code/tg/dataloader.py:17-27)."""
+    return split_batch(B, shard_graph_ranges(graph_node_counts(B), world_size))

@@ -1,0 +1,71 @@
+"""Graph-sharded data parallelism for the level sweep: one process per GPU (torch.distributed, NCCL over
+NVLink on the box; gloo in the CPU tests).
+
+Replaces the reference's single-process `DataParallel` (ogbg-code/tg/data_parallel.py:41-82 with the node-balanced
+`Collater`, ogbg-code/tg/dataloader.py:17-33; D-VAE: dvae/util.py:667-683): graphs of a batch are independent
+connected components, so the forward needs NO collective — each rank sweeps its own contiguous, node-balanced
+range of graphs and keeps its readout rows. Training needs exactly one all-reduce (sum) of the flat fp32
+gradient buffer per step (`allreduce_gradients`), which is the only data-path collective of this package.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .data import DagBatch, graph_node_counts, select_graphs, shard_graph_ranges
+
+
+def rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_for_rank(B: DagBatch, rank: Optional[int] = None, world_size: Optional[int] = None):
+    """-> (sub-batch of this rank, range of global graph ids it owns). Every rank computes the same partition
+    from the node counts (deterministic, no communication)."""
+    r, w = rank_world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    ranges = shard_graph_ranges(graph_node_counts(B), world_size)
+    return select_graphs(B, ranges[rank]), ranges[rank]
+
+
+def gather_rows(local: torch.Tensor, rows_per_rank: Sequence[int], group=None) -> torch.Tensor:
+    """all-gather variable-length row blocks (readouts / predictions) in rank order — used by evaluation and the
+    tests; not part of the timed forward."""
+    _, w = rank_world(group)
+    if w == 1:
+        return local
+    width = local.shape[1]
+    mx = max(rows_per_rank)
+    pad = local.new_zeros(mx, width)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:n] for b, n in zip(bufs, rows_per_rank)])
+
+
+def allreduce_gradients(params, group=None, average: bool = False) -> int:
+    """One all-reduce(sum) over a flat fp32 buffer of every gradient (the reference reduce-adds replicas'
+    gradients onto GPU 0 inside nn.DataParallel's backward, tg/data_parallel.py:59-62). Returns the number of
+    elements reduced. Loss is a mean over graphs, so callers scale by shard size / global batch before backward
+    (or pass average=True for equal shards)."""
+    r, w = rank_world(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(w)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off: off + n].view_as(g))
+        off += n
+    return int(flat.numel())
