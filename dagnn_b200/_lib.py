@@ -18,7 +18,7 @@ SOURCES = ["abi.cu", "schedule.cu", "embed_readout.cu", "pack.cu", "level_sweep.
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 vp = C.c_void_p
 
@@ -44,14 +44,14 @@ class DagnnPackLayout(C.Structure):
 class DagnnSweepArgs(C.Structure):
     _fields_ = [
         ("sched", C.POINTER(DagnnSchedule)),
-        ("lvl_off_host", C.POINTER(C.c_int32) * MAX_DIRS),
-        ("num_levels", C.c_int32), ("num_layers", C.c_int32),
+        ("num_layers", C.c_int32),
         ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32),
         ("X", vp), ("ldx", C.c_int64),
         ("Hs", (vp * MAX_LAYERS) * MAX_DIRS),
         ("ldh", C.c_int64),
         ("packed", (vp * MAX_LAYERS) * MAX_DIRS),
         ("use_edge_attr", C.c_int32),
+        ("workspace", vp), ("workspace_bytes", C.c_size_t), ("trace", vp),
     ]
 
 
@@ -71,6 +71,8 @@ EXPORTS = {
     "dagnn_schedule_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DagnnSchedule), vp, C.c_size_t, vp]),
     "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),
     "dagnn_pack_params_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(DagnnPackLayout), vp, vp]),
+    "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),

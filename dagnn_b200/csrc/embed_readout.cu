@@ -43,29 +43,66 @@ struct ReadoutArgs {
   const int* gptr;
 };
 
-// grid (B, nblocks, column chunks of 128): thread c owns one output column, walks the graph's node range.
-__global__ void __launch_bounds__(128) k_readout(const __grid_constant__ ReadoutArgs a, float* __restrict__ out, int64_t ldo) {
+// grid (B, nblocks, column chunks of 128), 256 threads: warp w scans nodes [v0 + 32w, v0 + 32w + 32) (+256 ...) of the
+// graph — lane j tests node j of the chunk (filter, position lookup), the selected ones are then read row by row with
+// every lane owning 4 columns (coalesced 128-byte segments, independent loads in flight); warps combine through smem.
+__global__ void __launch_bounds__(256) k_readout(const __grid_constant__ ReadoutArgs a, float* __restrict__ out, int64_t ldo) {
+  __shared__ float part[8][128];
+  __shared__ int pcnt[8];
   const int g = blockIdx.x;
   const DagnnReadoutBlock& b = a.blk[blockIdx.y];
-  const int c = blockIdx.z * 128 + threadIdx.x;
-  if (c >= b.width) return;
+  const int c0 = blockIdx.z * 128;
+  if (c0 >= b.width) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v0 = a.gptr[g], v1 = a.gptr[g + 1];
   const int* pos = b.index_mode ? a.pos[b.dir] : nullptr;
-  float acc = (a.pool == 0) ? -INFINITY : 0.f;
-  int cnt = 0;
   int vb = v0, ve = v1;
   if (b.filter == 2) vb = max(v0, v1 - 1);
   if (b.filter == 3) ve = min(v1, v0 + 1);
-  for (int v = vb; v < ve; ++v) {
-    if (b.filter == 1 && b.filter_lvl[v] != 0) continue;
-    const size_t row = pos ? (size_t)pos[v] : (size_t)v;
-    const float h = b.src[row * b.ld + c];
-    acc = (a.pool == 0) ? fmaxf(acc, h) : acc + h;
-    ++cnt;
+  const bool is_max = a.pool == 0;
+  float acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = is_max ? -INFINITY : 0.f;
+  int cnt = 0;
+  for (int base = vb + 32 * warp; base < ve; base += 256) {
+    const int v = base + lane;
+    bool sel = v < ve;
+    if (sel && b.filter == 1) sel = b.filter_lvl[v] == 0;
+    const long long row = sel ? (pos ? (long long)pos[v] : (long long)v) : 0;
+    unsigned m = __ballot_sync(0xffffffffu, sel);
+    cnt += __popc(m);
+    while (m) {
+      const int j0 = __ffs(m) - 1;
+      m &= m - 1;
+      const long long r = __shfl_sync(0xffffffffu, row, j0);
+      const float* srow = b.src + (size_t)r * b.ld + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        if (c0 + c < b.width) {
+          const float h = __ldcg(srow + c);
+          acc[j] = is_max ? fmaxf(acc[j], h) : acc[j] + h;
+        }
+      }
+    }
   }
-  if (cnt == 0) acc = 0.f;
-  else if (a.pool == 1) acc = acc / (float)cnt;
-  out[(size_t)g * ldo + b.out_col + c] = acc;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) part[warp][lane + 32 * j] = acc[j];
+  if (lane == 0) pcnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float r = part[0][c];
+    int n = pcnt[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      r = is_max ? fmaxf(r, part[w][c]) : r + part[w][c];
+      n += pcnt[w];
+    }
+    if (n == 0) r = 0.f;
+    else if (a.pool == 1) r = r / (float)n;
+    if (c0 + c < b.width) out[(size_t)g * ldo + b.out_col + c0 + c] = r;
+  }
 }
 
 }  // namespace dagnn
@@ -104,6 +141,6 @@ extern "C" int dagnn_readout_f32(const DagnnSchedule* s, const DagnnReadoutBlock
     maxw = blocks[i].width > maxw ? blocks[i].width : maxw;
   }
   dim3 grid((unsigned)s->B, (unsigned)nblocks, (unsigned)ceil_div(maxw, 128));
-  k_readout<<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(a, out, ldo);
+  k_readout<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(a, out, ldo);
   return check_launch("k_readout");
 }

@@ -1,56 +1,66 @@
-// The DAGNN level sweep: one fused kernel per wavefront step.
+// The DAGNN level sweep as ONE persistent cooperative kernel (one CTA per SM, grid barrier per wavefront step).
 //
-// A tile = (direction d, layer i, level l, BM consecutive positions of the level, one 128-unit slice of H).
+// Wavefront step s runs every (direction d, layer i, level l) with l + i == s: (l, i) depends on (l, i-1) [its
+// input rows] and on (< l, i) [predecessor states], both finished in earlier steps. The sequential depth is
+// L + layers - 1 grid barriers instead of L * layers * dirs kernel chains, and nothing on the host depends on the
+// level sizes: level offsets and the level count are read from device memory (no host sync in a forward).
+//
+// Work unit = tile (d, i, l, BM consecutive positions of the level, one 32-unit slice of H); the tiles of a step
+// are dealt round-robin to the CTAs. Per tile:
 //   phase 1  gather     : per node, stream its in-edge CSR row, online-softmax the additive-attention scores
-//                         (warp-reduced dot with the key vector + edge-type term), accumulate the weighted
-//                         predecessor rows -> m_v; copy the node's input row. Both land in shared memory as
-//                         the A tile [BM, Kin | Kh] — the aggregate never goes back to HBM.
-//   phase 2  gate GEMM  : [BM, Kin+Kh] x packed GRU weights [Kin+Kh, 3 x 128]; the weight stream is one
-//                         contiguous run per slice, brought in by cp.async.bulk (UBLKCP) into a 3-stage
-//                         mbarrier ring; FP32 FFMA register tiles (exact fp32 — see DESIGN.md for why not
-//                         single-pass TF32).
-//   phase 3  epilogue   : sigmoid/tanh/blend in registers, coalesced float4 store of the new state rows.
-// Wavefront: step s runs every (d, i, l) with l + i == s in ONE grid, so the sequential depth is
-// L + layers - 1 launches instead of L * layers * dirs.
+//                         (warp-reduced dot with the key vector + edge-type term [+ vertex-id term]) and accumulate
+//                         the weighted predecessor rows -> m_v; copy the node's input row. Both land in shared
+//                         memory as the A tile [BM, Kin | Kh] — the aggregate never goes back to HBM.
+//   phase 2  gate GEMM  : [BM, Kin+Kh] x packed GRU weights [Kin+Kh, 3 x 32]; the weight stream of a slice is one
+//                         contiguous run, brought in by cp.async.bulk (UBLKCP) into a multi-stage mbarrier ring that
+//                         keeps running across tiles; FP32 FFMA (exact fp32: DESIGN.md §3.3). Thread = one hidden
+//                         unit x 3 gates, looping over R rows of the tile: weights are read from shared memory once
+//                         per thread as float4 over k, A values are warp-wide broadcasts -> 12 FMA per smem wavefront.
+//   phase 3  epilogue   : sigmoid/tanh/blend in registers, 128-bit stores of the new state rows.
+// States written in one step are read in later steps by OTHER CTAs: all state reads use ld.global.cg (L2), the
+// barrier is the cooperative-groups pattern (bar.sync; fence; atomic; spin on ld.acquire; bar.sync).
 #include "common.cuh"
 
 namespace dagnn {
 
-constexpr int BN = DAGNN_UNIT_SLICE;            // hidden units per slice
-constexpr int BK = DAGNN_K_BLOCK;               // K rows per weight stage
+constexpr int US = DAGNN_UNIT_SLICE;            // hidden units per slice (32)
+constexpr int BK = DAGNN_K_BLOCK;               // K rows per weight stage (16)
 constexpr int kThreads = 256;
-constexpr int kStages = 3;
-constexpr int kWStageFloats = BK * 3 * BN;      // 6144
-constexpr int kWStageBytes = kWStageFloats * 4; // 24576
-constexpr int kMaxSeg = DAGNN_MAX_DIRS * DAGNN_MAX_LAYERS;
+constexpr int kMaxStages = 8;
+constexpr int kWSliceFloats = BK * 3 * US;      // 1536 floats = one k-block of one 32-unit slice
+constexpr int kWSliceBytes = kWSliceFloats * 4; // 6144
+constexpr int kWStageFloats = 2 * kWSliceFloats; // a ring stage holds up to two slices (64-unit tiles)
 constexpr int kBarBytes = 128;
 constexpr int kMaxSmem = 232448;                // 227 KB opt-in limit per CTA on sm_100
 
-struct Seg {
-  const float* inp;      // X (node order, rows through perm) or H[d][i-1] (position order)
-  const int* perm;       // position -> node id, or nullptr when inp is already in position order
-  long long ld_inp;
-  const float* Hcur;     // H[d][i]: predecessor rows are read here ...
-  float* Hout;           // ... and this level's rows are written here (same buffer)
-  const int* rowptr;
-  const int* col;
-  const float* eattr;    // [E,2] in CSR order or nullptr
-  const int* perm_vid;   // position -> node id for the vertex-id term, or nullptr
-  const float* w;        // packed weights  [NS][Kin+Kh][3][128]
-  const float* bias;     // [4][NS*128]
-  const float* wk;       // [NS*128]
-  const float* attnc;    // [4]
-  const float* vidk;     // [nvid]
-  int pos0, n_nodes;     // positions [pos0, pos0 + n_nodes) = this level
-  int Din, Kin;
-  int level0;            // 1: hidden = 0, no aggregation, K = Kin
-  int tile_begin;        // first tile (block) index of this segment inside the step's grid
+struct DirP {
+  const int* perm;      // position -> node id
+  const int* rowptr;    // [N+1] CSR rows by position
+  const int* col;       // [E] neighbour position
+  const float* eattr;   // [E,2] in CSR order or nullptr
+  const int* lvl_off;   // [max_levels+1] first position of each level
 };
-
-struct StepArgs {
-  int nseg, H, Hq, Kh, NS, nvid, use_ea, pad_;
-  long long ldh;
-  Seg seg[kMaxSeg];
+struct LayP {
+  float* Hs;            // H[d][i], [N, ldh] position order: predecessor rows read, this level's rows written
+  const float* w;       // packed weights [NS][Kin+Kh][3][US]
+  const float* bias;    // [4][NS*US]
+  const float* wk;      // [NS*US]
+  const float* attnc;   // [4]
+  const float* vidk;    // [nvid]
+};
+struct SweepP {
+  int dirs, layers, H, Hq, Kh, NS, nvid, use_ea;
+  int Din0, Kin0;       // layer 0 input width and its padded K; layers > 0 take H / Kh
+  int allow64, stages;
+  int upc, SP, nsmall, ldag;   // weight-stationary path: units per CTA (0 = off), CTAs per (d,i) pair, row threshold, scratch ld
+  float* Ag;            // [pairs][nsmall][ldag] gathered A rows of the small segments of the current step
+  long long ldh, ldx;
+  const float* X;       // [N, ldx] node order (rows through perm)
+  const int* summary;   // [0] number of levels of direction 0, [2] schedule status
+  unsigned int* bar;    // grid barrier counter (zeroed by the launcher)
+  long long* trace;     // optional [steps][grid][8] clock64 stamps (dagnn_sweep_trace_bytes), nullptr = off
+  DirP dir[DAGNN_MAX_DIRS];
+  LayP lay[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,6 +85,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of the (cooperative, co-resident) grid; `target` = arrivals expected so far
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_u32(bar) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
@@ -82,71 +108,150 @@ __device__ __forceinline__ void fma4(float (&acc)[4], float a, const float4& w) 
   acc[0] = fmaf(a, w.x, acc[0]); acc[1] = fmaf(a, w.y, acc[1]); acc[2] = fmaf(a, w.z, acc[2]); acc[3] = fmaf(a, w.w, acc[3]);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-// one BK-deep block of the gate GEMM. IN: the k rows belong to the input part (n-gate -> acc_n) else to the
-// hidden part (n-gate -> acc_h). A0 points at this thread's first row, column kb*BK.
-template <int TM, bool IN>
-__device__ __forceinline__ void mac_block(const float* __restrict__ W, const float* __restrict__ A0, int row_stride, int tx,
-                                          float (&acc_r)[TM][4], float (&acc_z)[TM][4], float (&acc_n)[TM][4],
-                                          float (&acc_h)[TM][4]) {
+// one BK-deep block of the gate GEMM for this thread's unit (3 gates) x R rows. W: this slice's stage
+// [4 kq][3 gates][32 units][4 k] floats; A0: first row of the thread's row group at the block's first k column.
+// IN: the k rows belong to the input part (n-gate -> acc_n) else to the hidden part (n-gate -> acc_h).
+template <int R, bool IN>
+__device__ __forceinline__ void mac_block(const float* __restrict__ W, const float* __restrict__ A0, int ldA, int lane,
+                                          float (&acc_r)[R], float (&acc_z)[R], float (&acc_n)[R], float (&acc_h)[R]) {
+  const float4* W4 = reinterpret_cast<const float4*>(W) + lane;
 #pragma unroll
-  for (int kk = 0; kk < BK; kk += 4) {
-    float4 av[TM];
+  for (int kq = 0; kq < BK / 4; ++kq) {
+    const float4 wr = W4[(kq * 3 + 0) * US];
+    const float4 wz = W4[(kq * 3 + 1) * US];
+    const float4 wn = W4[(kq * 3 + 2) * US];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) av[i] = *reinterpret_cast<const float4*>(A0 + i * row_stride + kk);
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      const float* wrow = W + (kk + k4) * (3 * BN) + tx * 4;
-      const float4 wr = *reinterpret_cast<const float4*>(wrow);
-      const float4 wz = *reinterpret_cast<const float4*>(wrow + BN);
-      const float4 wn = *reinterpret_cast<const float4*>(wrow + 2 * BN);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const float a = comp(av[i], k4);
-        fma4(acc_r[i], a, wr);
-        fma4(acc_z[i], a, wz);
-        if (IN) fma4(acc_n[i], a, wn); else fma4(acc_h[i], a, wn);
-      }
+    for (int r = 0; r < R; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(A0 + r * ldA + kq * 4);
+      acc_r[r] = fmaf(a.w, wr.w, fmaf(a.z, wr.z, fmaf(a.y, wr.y, fmaf(a.x, wr.x, acc_r[r]))));
+      acc_z[r] = fmaf(a.w, wz.w, fmaf(a.z, wz.z, fmaf(a.y, wz.y, fmaf(a.x, wz.x, acc_z[r]))));
+      if (IN) acc_n[r] = fmaf(a.w, wn.w, fmaf(a.z, wn.z, fmaf(a.y, wn.y, fmaf(a.x, wn.x, acc_n[r]))));
+      else acc_h[r] = fmaf(a.w, wn.w, fmaf(a.z, wn.z, fmaf(a.y, wn.y, fmaf(a.x, wn.x, acc_h[r]))));
     }
   }
 }
 
-template <int BM>
-__global__ void __launch_bounds__(kThreads, 1) k_level_step(const __grid_constant__ StepArgs a) {
-  constexpr int TM = BM / 8;
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  float* Ws = reinterpret_cast<float*>(smem + kBarBytes);
-  float* As = Ws + kStages * kWStageFloats;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+struct TileCtx {
+  uint64_t* bars;
+  float* Ws;
+  float* As;
+  long long* tr; // trace slot of the current (step, CTA) while its first tile runs, else nullptr
+  uint32_t it;   // cumulative weight-ring iteration count of this CTA (stage = it % kStages, parity = (it / kStages) & 1)
+};
 
-  int si = 0;
-#pragma unroll 1
-  while (si + 1 < a.nseg && (int)blockIdx.x >= a.seg[si + 1].tile_begin) ++si;
-  const Seg& S = a.seg[si];
-  const int t = (int)blockIdx.x - S.tile_begin;
-  const int nt = t / a.NS, sl = t - nt * a.NS;
-  const int p0 = S.pos0 + nt * BM;
-  const int nvalid = min(BM, S.n_nodes - nt * BM);
-  const int Kin = S.Kin, Kh = a.Kh, Hq = a.Hq;
+// gather + attention for one node (one warp): writes the A row [inp | m_v]
+__device__ __forceinline__ void gather_row(const SweepP& P, const DirP& D, const LayP& Lp, const float* __restrict__ inp,
+                                           long long ld_inp, bool inp_via_perm, int Din, int Kin, bool level0, int p, int pos0,
+                                           float* __restrict__ arow, const float4 (&wk4)[4], float ca0, float ca1, bool use_ea,
+                                           int lane) {
+  const int Hq = P.Hq, Kh = P.Kh;
+  const float* src = inp + (size_t)(inp_via_perm ? D.perm[p] : p) * ld_inp;
+  for (int c = lane; c < Kin; c += 32) arow[c] = (c < Din) ? __ldcg(src + c) : 0.f;
+  if (level0) return;
+  const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
+  float mx = -INFINITY, lsum = 0.f;
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* Hcur = Lp.Hs;
+  const long long ldh = P.ldh;
+  for (int eb = e0; eb < e1; eb += 32) {
+    // one coalesced load of up to 32 neighbour positions (+ edge attributes), then broadcast per edge
+    const int ne = min(32, e1 - eb);
+    int my_sp = 0;
+    float my_bias = 0.f;
+    if (lane < ne) {
+      my_sp = D.col[eb + lane];
+      if (use_ea) {
+        const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + eb + lane);
+        my_bias = ca0 * ea.x + ca1 * ea.y;
+      }
+      if (P.nvid > 0) my_bias += __ldg(Lp.vidk + (D.perm[my_sp] % P.nvid));
+    }
+    float4 row[4], nrow[4];
+    int sp = __shfl_sync(0xffffffffu, my_sp, 0);
+    bool valid = sp < pos0;   // predecessor sits in an earlier level -> its state exists
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * lane + 128 * j;
+      row[j] = (valid && c < Hq) ? ldcg4(Hcur + (size_t)sp * ldh + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int q = 0; q < ne; ++q) {
+      // prefetch the next edge's row while this one is reduced
+      if (q + 1 < ne) {
+        const int spn = __shfl_sync(0xffffffffu, my_sp, q + 1);
+        const bool vn = spn < pos0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * lane + 128 * j;
+          nrow[j] = (vn && c < Hq) ? ldcg4(Hcur + (size_t)spn * ldh + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dot += dot4(row[j], wk4[j]);
+      const float s = warp_sum(dot) + __shfl_sync(0xffffffffu, my_bias, q);
+      const float mnew = fmaxf(mx, s);
+      const float sc = expf(mx - mnew), pe = expf(s - mnew);
+      lsum = lsum * sc + pe;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = acc[j].x * sc + pe * row[j].x; acc[j].y = acc[j].y * sc + pe * row[j].y;
+        acc[j].z = acc[j].z * sc + pe * row[j].z; acc[j].w = acc[j].w * sc + pe * row[j].w;
+      }
+      mx = mnew;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) row[j] = nrow[j];
+    }
+  }
+  const float inv = (e1 > e0) ? 1.f / (lsum + 1e-16f) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * lane + 128 * j;
+    if (c < Kh) {
+      float4 o = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+      if (c >= Hq) o = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(arow + Kin + c) = o;
+    }
+  }
+}
+
+// one tile: rows [p0, p0+nvalid) of level `l` (first position pos0) of (d, i), unit slices [sl0, sl0 + NSL)
+// R rows per thread, NSL 32-unit slices per tile: BM = R * 8 / NSL rows.
+template <int R, int NSL>
+__device__ __forceinline__ void process_tile(const SweepP& P, int d, int i, bool level0, int pos0, int p0, int nvalid, int sl0,
+                                             TileCtx& T) {
+  constexpr int BM = R * 8 / NSL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DirP& D = P.dir[d];
+  const LayP& Lp = P.lay[d][i];
+  const int Din = (i == 0) ? P.Din0 : P.H;
+  const int Kin = (i == 0) ? P.Kin0 : P.Kh;
+  const int Kh = P.Kh, Hq = P.Hq;
   const int ldA = Kin + Kh + 4;
   const int nkb_in = Kin / BK;
-  const int nkb = nkb_in + (S.level0 ? 0 : Kh / BK);
-  const float* wsrc = S.w + (size_t)sl * (Kin + Kh) * (3 * BN);
-  const long long ldh = a.ldh;
+  const int nkb = nkb_in + (level0 ? 0 : Kh / BK);
+  const int S = P.stages;
+  const int nsl = min(NSL, P.NS - sl0);                          // slices of this tile that exist
+  const size_t slice_stride = (size_t)(Kin + Kh) * (3 * US);     // floats per slice in the packed stream
+  const float* wsrc = Lp.w + (size_t)sl0 * slice_stride;
+  float* As = T.As;
 
+  auto issue = [&](int kb) {                                     // tid 0: bring k-block kb of the tile's slices
+    const uint32_t st = (T.it + kb) % S;
+    const uint32_t bar = smem_u32(&T.bars[st]);
+    mbar_expect_tx(bar, (uint32_t)(nsl * kWSliceBytes));
+    for (int q = 0; q < nsl; ++q)
+      bulk_g2s(smem_u32(T.Ws + st * kWStageFloats + q * kWSliceFloats), wsrc + q * slice_stride + (size_t)kb * kWSliceFloats,
+               kWSliceBytes, bar);
+  };
+
+  __syncthreads();   // previous tile: ring drained, A tile and epilogue reads done
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int kb = 0; kb < kStages - 1 && kb < nkb; ++kb) {
-      mbar_expect_tx(smem_u32(&bars[kb]), kWStageBytes);
-      bulk_g2s(smem_u32(Ws + kb * kWStageFloats), wsrc + (size_t)kb * kWStageFloats, kWStageBytes, smem_u32(&bars[kb]));
-    }
+    const int npre = min(S - 1, nkb);
+    for (int kb = 0; kb < npre; ++kb) issue(kb);
   }
 
   // ---------------- phase 1: gather + attention -> A tile ----------------
@@ -155,227 +260,382 @@ __global__ void __launch_bounds__(kThreads, 1) k_level_step(const __grid_constan
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = 4 * lane + 128 * j;
-      wk4[j] = (c < Hq) ? __ldg(reinterpret_cast<const float4*>(S.wk + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wk4[j] = (c < Hq && !level0) ? __ldg(reinterpret_cast<const float4*>(Lp.wk + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const bool use_ea = a.use_ea && S.eattr != nullptr;
-    const float ca0 = use_ea ? __ldg(S.attnc) : 0.f, ca1 = use_ea ? __ldg(S.attnc + 1) : 0.f;
+    const bool use_ea = P.use_ea && D.eattr != nullptr;
+    const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
+    const float* inp = (i == 0) ? P.X : P.lay[d][i - 1].Hs;
+    const long long ld_inp = (i == 0) ? P.ldx : P.ldh;
     for (int m = warp; m < BM; m += 8) {
       float* arow = As + m * ldA;
       if (m >= nvalid) {
         for (int c = lane; c < Kin + Kh; c += 32) arow[c] = 0.f;
         continue;
       }
-      const int p = p0 + m;
-      const float* src = S.inp + (size_t)(S.perm ? S.perm[p] : p) * S.ld_inp;
-      for (int c = lane; c < Kin; c += 32) arow[c] = (c < S.Din) ? __ldcg(src + c) : 0.f;
-      if (S.level0) continue;
-      const int e0 = S.rowptr[p], e1 = S.rowptr[p + 1];
-      float mx = -INFINITY, lsum = 0.f;
-      float4 acc[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int sp_next = (e0 < e1) ? S.col[e0] : 0;
-      for (int e = e0; e < e1; ++e) {
-        const int sp = sp_next;
-        if (e + 1 < e1) sp_next = S.col[e + 1];
-        const bool valid = sp < S.pos0;   // predecessor sits in an earlier level -> its state exists
-        float4 row[4];
-        float dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 4 * lane + 128 * j;
-          row[j] = (valid && c < Hq) ? ldcg4(S.Hcur + (size_t)sp * ldh + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          dot += row[j].x * wk4[j].x + row[j].y * wk4[j].y + row[j].z * wk4[j].z + row[j].w * wk4[j].w;
-        }
-        float s = warp_sum(dot);
-        if (use_ea) {
-          const float2 ea = __ldg(reinterpret_cast<const float2*>(S.eattr) + e);
-          s += ca0 * ea.x + ca1 * ea.y;
-        }
-        if (a.nvid > 0) s += __ldg(S.vidk + (S.perm_vid[sp] % a.nvid));
-        const float mnew = fmaxf(mx, s);
-        const float sc = expf(mx - mnew), pe = expf(s - mnew);
-        lsum = lsum * sc + pe;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[j].x = acc[j].x * sc + pe * row[j].x; acc[j].y = acc[j].y * sc + pe * row[j].y;
-          acc[j].z = acc[j].z * sc + pe * row[j].z; acc[j].w = acc[j].w * sc + pe * row[j].w;
-        }
-        mx = mnew;
-      }
-      const float inv = (e1 > e0) ? 1.f / (lsum + 1e-16f) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = 4 * lane + 128 * j;
-        if (c < Kh) {
-          float4 o = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
-          if (c >= Hq) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(arow + Kin + c) = o;
-        }
-      }
+      gather_row(P, D, Lp, inp, ld_inp, i == 0, Din, Kin, level0, p0 + m, pos0, arow, wk4, ca0, ca1, use_ea, lane);
     }
   }
   __syncthreads();
 
   // ---------------- phase 2: gate GEMM ----------------
-  float acc_r[TM][4], acc_z[TM][4], acc_n[TM][4], acc_h[TM][4];
+  float acc_r[R], acc_z[R], acc_n[R], acc_h[R];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc_r[i][j] = acc_z[i][j] = acc_n[i][j] = acc_h[i][j] = 0.f;
+  for (int r = 0; r < R; ++r) acc_r[r] = acc_z[r] = acc_n[r] = acc_h[r] = 0.f;
 
-  const float* Arow0 = As + warp * ldA;
-  const int row_stride = 8 * ldA;
+  const int wu = warp % NSL;                  // which of the tile's slices this warp owns
+  const int row0 = (warp / NSL) * R;          // first row of this warp's row group
+  const bool active = wu < nsl;
+  const float* Arow0 = As + row0 * ldA;
 #pragma unroll 1
   for (int kb = 0; kb < nkb; ++kb) {
-    if (tid == 0) {
-      const int nb = kb + kStages - 1;
-      if (nb < nkb) {
-        const int s = nb % kStages;
-        mbar_expect_tx(smem_u32(&bars[s]), kWStageBytes);
-        bulk_g2s(smem_u32(Ws + s * kWStageFloats), wsrc + (size_t)nb * kWStageFloats, kWStageBytes, smem_u32(&bars[s]));
-      }
+    if (tid == 0 && kb + S - 1 < nkb) issue(kb + S - 1);
+    const uint32_t itk = T.it + kb;
+    const uint32_t st = itk % S;
+    mbar_wait(smem_u32(&T.bars[st]), (itk / S) & 1u);
+    if (active) {
+      const float* W = T.Ws + st * kWStageFloats + wu * kWSliceFloats;
+      if (kb < nkb_in) mac_block<R, true>(W, Arow0 + kb * BK, ldA, lane, acc_r, acc_z, acc_n, acc_h);
+      else mac_block<R, false>(W, Arow0 + kb * BK, ldA, lane, acc_r, acc_z, acc_n, acc_h);
     }
-    const int st = kb % kStages;
-    mbar_wait(smem_u32(&bars[st]), (uint32_t)((kb / kStages) & 1));
-    const float* W = Ws + st * kWStageFloats;
-    if (kb < nkb_in) mac_block<TM, true>(W, Arow0 + kb * BK, row_stride, lane, acc_r, acc_z, acc_n, acc_h);
-    else mac_block<TM, false>(W, Arow0 + kb * BK, row_stride, lane, acc_r, acc_z, acc_n, acc_h);
     __syncthreads();
   }
+  T.it += nkb;
 
   // ---------------- phase 3: GRU pointwise + store ----------------
-  const int u = sl * BN + lane * 4;
-  if (u < Hq) {
-    const int HP = a.NS * BN;
-    const float4 br = __ldg(reinterpret_cast<const float4*>(S.bias + u));
-    const float4 bz = __ldg(reinterpret_cast<const float4*>(S.bias + HP + u));
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(S.bias + 2 * HP + u));
-    const float4 bh = __ldg(reinterpret_cast<const float4*>(S.bias + 3 * HP + u));
+  const int u = (sl0 + wu) * US + lane;
+  if (active && u < Hq) {
+    const int HP = P.NS * US;
+    const float br = __ldg(Lp.bias + u), bz = __ldg(Lp.bias + HP + u), bi = __ldg(Lp.bias + 2 * HP + u),
+                bh = __ldg(Lp.bias + 3 * HP + u);
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = warp + 8 * i;
+    for (int r = 0; r < R; ++r) {
+      const int m = row0 + r;
       if (m < nvalid) {
-        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!S.level0) hp = *reinterpret_cast<const float4*>(As + m * ldA + Kin + u);
-        float o[4];
-        const float hpv[4] = {hp.x, hp.y, hp.z, hp.w};
-        const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
-        const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float r = sigmoidf_(acc_r[i][j] + brv[j]);
-          const float z = sigmoidf_(acc_z[i][j] + bzv[j]);
-          const float n = tanhf(acc_n[i][j] + biv[j] + r * (acc_h[i][j] + bhv[j]));
-          o[j] = n + z * (hpv[j] - n);
-        }
-        *reinterpret_cast<float4*>(S.Hout + (size_t)(p0 + m) * ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
+        const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
+        const float rg = sigmoidf_(acc_r[r] + br);
+        const float zg = sigmoidf_(acc_z[r] + bz);
+        const float ng = tanhf(acc_n[r] + bi + rg * (acc_h[r] + bh));
+        Lp.Hs[(size_t)(p0 + m) * P.ldh + u] = ng + zg * (hp - ng);
       }
     }
   }
 }
 
-static size_t smem_for(int BM, int Kin, int Kh) {
-  return (size_t)kBarBytes + (size_t)kStages * kWStageBytes + (size_t)BM * (Kin + Kh + 4) * 4;
+// ------------------------------------------------------------------------------------------------------------
+// Weight-stationary path for SMALL segments (n <= nsmall rows): CTA b owns `upc` hidden units of pair q = b / SP for
+// the whole sweep and keeps that slice of the GRU weights resident in shared memory ([K/4][3 gates][upc] float4 over
+// k). A step then costs no weight traffic at all: phase G spreads the rows of all small segments over every warp of
+// the grid (gather + attention -> A rows in an L2-resident scratch), grid barrier, phase M: every owner CTA pulls its
+// segment's A rows into shared memory and computes its units for all rows.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_resident(const SweepP& P, int q, int slot, float4* __restrict__ Wres) {
+  const int d = q / P.layers, i = q - d * P.layers;
+  const int Kin = (i == 0) ? P.Kin0 : P.Kh;
+  const int K = Kin + P.Kh, nkb = K / BK;
+  const int unit0 = slot * P.upc, sl = unit0 / US, uo = unit0 - sl * US;
+  const float4* src = reinterpret_cast<const float4*>(P.lay[d][i].w) + (size_t)sl * nkb * (BK / 4) * 3 * US;
+  const int total = (K / 4) * 3 * P.upc;
+  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+    const int u = idx % P.upc, g = (idx / P.upc) % 3, kqg = idx / (3 * P.upc);
+    Wres[idx] = __ldg(src + ((size_t)kqg * 3 + g) * US + uo + u);     // packed: [kb][kq][g][32 units] float4
+  }
 }
 
-template <int BM>
-static int launch_step(const StepArgs& a, int tiles, size_t smem, cudaStream_t st) {
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_level_step<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    configured[dev] = true;
-  } else if (dev >= 64) {
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_level_step<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+// phase M for one chunk of <= 32*T rows already staged in As. Thread = (unit lane u8, row slot); UPT units per thread.
+template <int T, int UPT>
+__device__ __forceinline__ void stationary_chunk(const SweepP& P, const LayP& Lp, const float4* __restrict__ Wres, const float* As,
+                                                 int ldA, int Kin, bool level0, int rows, int prow0, int unit0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u8 = lane & 7, slot = warp * 4 + (lane >> 3);
+  const int upc = P.upc;
+  const int nkq_in = Kin / 4, nkq = nkq_in + (level0 ? 0 : P.Kh / 4);
+  float acc_r[T][UPT], acc_z[T][UPT], acc_n[T][UPT], acc_h[T][UPT];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) acc_r[t][j] = acc_z[t][j] = acc_n[t][j] = acc_h[t][j] = 0.f;
+  const float* A0 = As + slot * ldA;
+  if (slot < rows) {      // rows beyond the chunk: whole quarter-warps idle
+#pragma unroll 2
+    for (int kq = 0; kq < nkq; ++kq) {
+      float4 a[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) a[t] = *reinterpret_cast<const float4*>(A0 + t * 32 * ldA + kq * 4);
+      const float4* w = Wres + (size_t)kq * 3 * upc + u8;
+      const bool in = kq < nkq_in;
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) {
+        const float4 wr = w[8 * j], wz = w[upc + 8 * j], wn = w[2 * upc + 8 * j];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          acc_r[t][j] = fmaf(a[t].w, wr.w, fmaf(a[t].z, wr.z, fmaf(a[t].y, wr.y, fmaf(a[t].x, wr.x, acc_r[t][j]))));
+          acc_z[t][j] = fmaf(a[t].w, wz.w, fmaf(a[t].z, wz.z, fmaf(a[t].y, wz.y, fmaf(a[t].x, wz.x, acc_z[t][j]))));
+          const float nn = fmaf(a[t].w, wn.w, fmaf(a[t].z, wn.z, fmaf(a[t].y, wn.y, a[t].x * wn.x)));
+          if (in) acc_n[t][j] += nn; else acc_h[t][j] += nn;
+        }
+      }
+    }
+    const int HP = P.NS * US;
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) {
+      const int u = unit0 + u8 + 8 * j;
+      if (u < P.Hq) {
+        const float br = __ldg(Lp.bias + u), bz = __ldg(Lp.bias + HP + u), bi = __ldg(Lp.bias + 2 * HP + u),
+                    bh = __ldg(Lp.bias + 3 * HP + u);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int m = slot + 32 * t;
+          if (m < rows) {
+            const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
+            const float rg = sigmoidf_(acc_r[t][j] + br);
+            const float zg = sigmoidf_(acc_z[t][j] + bz);
+            const float ng = tanhf(acc_n[t][j] + bi + rg * (acc_h[t][j] + bh));
+            Lp.Hs[(size_t)(prow0 + m) * P.ldh + u] = ng + zg * (hp - ng);
+          }
+        }
+      }
+    }
   }
-  k_level_step<BM><<<tiles, kThreads, smem, st>>>(a);
-  return check_launch("k_level_step");
 }
+
+template <int UPT>
+__device__ __forceinline__ void stationary_segment(const SweepP& P, int q, int slot, bool level0, int pos0, int n,
+                                                   const float4* __restrict__ Wres, float* As) {
+  const int d = q / P.layers, i = q - d * P.layers;
+  const LayP& Lp = P.lay[d][i];
+  const int Kin = (i == 0) ? P.Kin0 : P.Kh;
+  const int Kuse = Kin + (level0 ? 0 : P.Kh);
+  const int ldA = Kin + P.Kh + 4;
+  const int chunk = P.allow64 ? 64 : 32;
+  const float* Aq = P.Ag + (size_t)q * P.nsmall * P.ldag;
+  const int k4n = Kuse / 4;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int rows = min(chunk, n - c0);
+    __syncthreads();                       // As free (previous chunk / previous tile)
+    for (int idx = threadIdx.x; idx < rows * k4n; idx += kThreads) {
+      const int r = idx / k4n, c4 = idx - r * k4n;
+      *reinterpret_cast<float4*>(As + r * ldA + 4 * c4) = ldcg4(Aq + (size_t)(c0 + r) * P.ldag + 4 * c4);
+    }
+    __syncthreads();
+    if (rows > 32) stationary_chunk<2, UPT>(P, Lp, Wres, As, ldA, Kin, level0, rows, pos0 + c0, slot * P.upc);
+    else stationary_chunk<1, UPT>(P, Lp, Wres, As, ldA, Kin, level0, rows, pos0 + c0, slot * P.upc);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_sweep_persistent(const __grid_constant__ SweepP P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  TileCtx T;
+  T.bars = reinterpret_cast<uint64_t*>(smem);
+  T.Ws = reinterpret_cast<float*>(smem + kBarBytes);
+  T.As = T.Ws + P.stages * kWStageFloats;
+  T.it = 0;
+  T.tr = nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kMaxStages; ++s) mbar_init(smem_u32(&T.bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (P.summary[2] != 0) return;               // schedule build flagged bad input: the host raises (uniform exit)
+  const int L = P.summary[0];
+  const int nsteps = L + P.layers - 1;
+  const int nseg = P.dirs * P.layers;
+  const int G = (int)gridDim.x;
+  const int ldAmax = max(P.Kin0, P.Kh) + P.Kh + 4;
+  float4* Wres = reinterpret_cast<float4*>(T.As + (size_t)(P.allow64 ? 64 : 32) * ldAmax);
+  // weight-stationary ownership
+  int my_q = -1, my_slot = 0;
+  if (P.upc > 0 && (int)blockIdx.x < nseg * P.SP) {
+    my_q = (int)blockIdx.x / P.SP;
+    my_slot = (int)blockIdx.x - my_q * P.SP;
+    load_resident(P, my_q, my_slot, Wres);
+  }
+  unsigned int nbar = 0;
+
+#pragma unroll 1
+  for (int s = 0; s < nsteps; ++s) {
+    long long* tr = P.trace ? P.trace + ((size_t)s * 256 + blockIdx.x) * 8 : nullptr;
+    if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; }
+    // ---- classify the segments of this step
+    const int NS2 = (P.NS + 1) / 2;
+    int tbig = 0, small_rows = 0;
+    unsigned small_mask = 0;
+    for (int q = 0; q < nseg; ++q) {
+      const int d = q / P.layers, i = q - d * P.layers, l = s - i;
+      if (l < 0 || l >= L) continue;
+      const int n = P.dir[d].lvl_off[l + 1] - P.dir[d].lvl_off[l];
+      if (n <= 0) continue;
+      if (P.upc > 0 && n <= P.nsmall) { small_mask |= 1u << q; small_rows += n; }
+      else tbig += ceil_div(n, 64) * NS2;
+    }
+    // ---- small segments, phase G: one row per warp, rows dealt over all warps of the grid
+    if (small_mask) {
+      int rbase = 0;
+      for (int q = 0; q < nseg; ++q) {
+        if (!(small_mask >> q & 1)) continue;
+        const int d = q / P.layers, i = q - d * P.layers, l = s - i;
+        const DirP& D = P.dir[d];
+        const LayP& Lp = P.lay[d][i];
+        const int pos0 = D.lvl_off[l], n = D.lvl_off[l + 1] - pos0;
+        const bool level0 = l == 0;
+        const int Din = (i == 0) ? P.Din0 : P.H, Kin = (i == 0) ? P.Kin0 : P.Kh;
+        const int W8 = G * 8;
+        int r = (((int)blockIdx.x + warp * G) - rbase % W8 + W8) % W8;     // warp-global id (CTA-minor) minus offset
+        if (r < n) {
+          float4 wk4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = 4 * lane + 128 * j;
+            wk4[j] = (c < P.Hq && !level0) ? __ldg(reinterpret_cast<const float4*>(Lp.wk + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const bool use_ea = P.use_ea && D.eattr != nullptr;
+          const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
+          const float* inp = (i == 0) ? P.X : P.lay[d][i - 1].Hs;
+          const long long ld_inp = (i == 0) ? P.ldx : P.ldh;
+          for (; r < n; r += W8)
+            gather_row(P, D, Lp, inp, ld_inp, i == 0, Din, Kin, level0, pos0 + r, pos0,
+                       P.Ag + ((size_t)q * P.nsmall + r) * P.ldag, wk4, ca0, ca1, use_ea, lane);
+        }
+        rbase += n;
+      }
+      if (tr && tid == 0) tr[1] = clock64();
+      grid_barrier(P.bar, ++nbar * (unsigned int)G);
+      if (tr && tid == 0) tr[2] = clock64();
+      // ---- phase M: my pair's segment, my units, resident weights
+      if (my_q >= 0 && (small_mask >> my_q & 1)) {
+        const int d = my_q / P.layers, i = my_q - d * P.layers, l = s - i;
+        const int pos0 = P.dir[d].lvl_off[l], n = P.dir[d].lvl_off[l + 1] - pos0;
+        if (P.upc == 8) stationary_segment<1>(P, my_q, my_slot, l == 0, pos0, n, Wres, T.As);
+        else if (P.upc == 16) stationary_segment<2>(P, my_q, my_slot, l == 0, pos0, n, Wres, T.As);
+        else stationary_segment<4>(P, my_q, my_slot, l == 0, pos0, n, Wres, T.As);
+      }
+      if (tr && tid == 0) tr[3] = clock64();
+    }
+    // ---- big segments: streamed-weight tiles dealt round-robin
+    const bool big = P.allow64 && tbig >= G;
+    const int bm = big ? 64 : 32;
+    int my_tiles = 0;
+    const int nsl_tile = big ? NS2 : P.NS;       // unit-slice tiles per row tile
+    int base = 0;
+    for (int q = 0; q < nseg; ++q) {
+      if (small_mask >> q & 1) continue;
+      const int d = q / P.layers, i = q - d * P.layers, l = s - i;
+      if (l < 0 || l >= L) continue;
+      const int pos0 = P.dir[d].lvl_off[l];
+      const int n = P.dir[d].lvl_off[l + 1] - pos0;
+      if (n <= 0) continue;
+      const int ntile = ceil_div(n, bm) * nsl_tile;
+      // my tiles of this segment: global tile ids g = base + t, g % G == (G - 1 - blockIdx.x): the CTAs without a
+      // stationary slice take tiles first
+      int t = ((G - 1 - (int)blockIdx.x) - base % G + G) % G;
+      for (; t < ntile; t += G) {
+        const int rt = t / nsl_tile, sl = t - rt * nsl_tile;
+        const int p0 = pos0 + rt * bm;
+        const int nvalid = min(bm, n - rt * bm);
+        if (big) process_tile<16, 2>(P, d, i, l == 0, pos0, p0, nvalid, 2 * sl, T);
+        else process_tile<4, 1>(P, d, i, l == 0, pos0, p0, nvalid, sl, T);
+        ++my_tiles;
+      }
+      base += ntile;
+    }
+    if (tr && tid == 0) { tr[4] = clock64(); tr[6] = my_tiles; tr[7] = (big ? 1 : 0) | (small_mask << 1); }
+    if (s + 1 < nsteps) grid_barrier(P.bar, ++nbar * (unsigned int)G);
+    if (tr && tid == 0) tr[5] = clock64();
+  }
+}
+
+static size_t smem_for(int BM, int Kin, int Kh, int stages, int upc = 0) {
+  return (size_t)kBarBytes + (size_t)stages * kWStageFloats * 4 + (size_t)BM * (Kin + Kh + 4) * 4 + (size_t)(Kin + Kh) * 3 * upc * 4;
+}
+constexpr int kNSmall = 256;      // segments with at most this many rows take the weight-stationary path
 
 }  // namespace dagnn
 
 using namespace dagnn;
 
+extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H) {
+  if (dirs < 1 || dirs > DAGNN_MAX_DIRS || layers < 1 || layers > DAGNN_MAX_LAYERS || Din < 1 || H < 1) return 0;
+  const int Kh = round_up(H, DAGNN_K_BLOCK), Kin0 = round_up(Din, DAGNN_K_BLOCK);
+  const size_t ldag = (size_t)(Kin0 > Kh ? Kin0 : Kh) + Kh;
+  return 256 + (size_t)dirs * layers * kNSmall * ldag * sizeof(float);
+}
+extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)max_steps * 256 * 8 * sizeof(long long); }
+
 extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   DAGNN_REQUIRE(A && A->sched, "sweep: null args");
   const DagnnSchedule* S = A->sched;
-  const int dirs = S->dirs, layers = A->num_layers, L = A->num_levels, H = A->H;
+  const int dirs = S->dirs, layers = A->num_layers, H = A->H;
   DAGNN_REQUIRE(layers >= 1 && layers <= DAGNN_MAX_LAYERS, "sweep: num_layers");
-  DAGNN_REQUIRE(L >= 1 && L <= S->max_levels, "sweep: num_levels");
   DAGNN_REQUIRE(A->X && A->ldx >= A->Din && A->Din > 0, "sweep: X");
   DAGNN_REQUIRE(A->ldh % 4 == 0 && A->ldh >= round_up(H, 4), "sweep: ldh must be a multiple of 4 and >= roundup(H,4)");
+  DAGNN_REQUIRE(A->workspace && A->workspace_bytes >= dagnn_sweep_workspace_bytes(dirs, layers, A->Din, H) &&
+                    ((uintptr_t)A->workspace & 255) == 0,
+                "sweep: workspace (dagnn_sweep_workspace_bytes, 256-byte aligned)");
   if (H < 1 || H > 512) return set_err(DAGNN_E_UNSUPPORTED, "sweep: hidden size %d not in [1,512]", H);
   if (A->nvid < 0) return set_err(DAGNN_E_INVALID, "sweep: nvid");
+  DagnnPackLayout lay0, layL;
+  if (int rc = dagnn_pack_layout(A->Din, H, A->nvid, &lay0)) return rc;
+  if (int rc = dagnn_pack_layout(H, H, A->nvid, &layL)) return rc;
+  SweepP P;
+  memset(&P, 0, sizeof(P));
+  P.dirs = dirs; P.layers = layers; P.H = H; P.Hq = round_up(H, 4); P.Kh = lay0.Kh; P.NS = lay0.NS; P.nvid = A->nvid;
+  P.use_ea = A->use_edge_attr; P.Din0 = A->Din; P.Kin0 = lay0.Kin;
+  P.ldh = A->ldh; P.ldx = A->ldx; P.X = A->X; P.summary = S->summary; P.bar = static_cast<unsigned int*>(A->workspace);
+  P.trace = static_cast<long long*>(A->trace);
   for (int d = 0; d < dirs; ++d) {
-    DAGNN_REQUIRE(A->lvl_off_host[d], "sweep: lvl_off_host");
+    DAGNN_REQUIRE(S->perm[d] && S->rowptr[d] && S->lvl_off[d] && (S->E == 0 || S->col[d]), "sweep: schedule arrays");
+    DAGNN_REQUIRE(!A->use_edge_attr || S->E == 0 || S->eattr[d], "sweep: schedule carries no edge attributes");
+    P.dir[d].perm = S->perm[d]; P.dir[d].rowptr = S->rowptr[d]; P.dir[d].col = S->col[d];
+    P.dir[d].eattr = A->use_edge_attr ? S->eattr[d] : nullptr; P.dir[d].lvl_off = S->lvl_off[d];
     for (int i = 0; i < layers; ++i) {
       DAGNN_REQUIRE(A->Hs[d][i] && ((uintptr_t)A->Hs[d][i] & 15) == 0, "sweep: state buffers must be 16-byte aligned");
       DAGNN_REQUIRE(A->packed[d][i] && ((uintptr_t)A->packed[d][i] & 15) == 0, "sweep: packed params must be 16-byte aligned");
-    }
-    DAGNN_REQUIRE(!A->use_edge_attr || S->E == 0 || S->eattr[d], "sweep: schedule carries no edge attributes");
-  }
-  DagnnPackLayout lay[2];
-  if (int rc = dagnn_pack_layout(A->Din, H, A->nvid, &lay[0])) return rc;
-  if (int rc = dagnn_pack_layout(H, H, A->nvid, &lay[1])) return rc;
-  const int Kh = lay[0].Kh, NS = lay[0].NS;
-  const int Kin_max = layers > 1 ? (lay[0].Kin > lay[1].Kin ? lay[0].Kin : lay[1].Kin) : lay[0].Kin;
-  if (smem_for(16, Kin_max, Kh) > (size_t)kMaxSmem) return set_err(DAGNN_E_UNSUPPORTED, "sweep: Din=%d too wide", A->Din);
-
-  const int nsteps = L + layers - 1;
-  for (int s = 0; s < nsteps; ++s) {
-    StepArgs a;
-    a.nseg = 0; a.H = H; a.Hq = round_up(H, 4); a.Kh = Kh; a.NS = NS; a.nvid = A->nvid; a.use_ea = A->use_edge_attr; a.pad_ = 0;
-    a.ldh = A->ldh;
-    int max_nodes = 0, kin_step = 0;
-    struct Pending { int d, i, l, n; } pend[kMaxSeg];
-    int np = 0;
-    for (int d = 0; d < dirs; ++d)
-      for (int i = 0; i < layers; ++i) {
-        const int l = s - i;
-        if (l < 0 || l >= L) continue;
-        const int n = A->lvl_off_host[d][l + 1] - A->lvl_off_host[d][l];
-        if (n <= 0) continue;
-        pend[np++] = {d, i, l, n};
-        max_nodes = n > max_nodes ? n : max_nodes;
-        const int kin = lay[i > 0].Kin;
-        kin_step = kin > kin_step ? kin : kin_step;
-      }
-    if (np == 0) continue;
-    int BM = 64;
-    if (max_nodes <= 16) BM = 16; else if (max_nodes <= 32) BM = 32;
-    while (BM > 16 && smem_for(BM, kin_step, Kh) > (size_t)kMaxSmem) BM >>= 1;
-    int tiles = 0;
-    for (int q = 0; q < np; ++q) {
-      const int d = pend[q].d, i = pend[q].i, l = pend[q].l;
-      const DagnnPackLayout& P = lay[i > 0];
-      Seg& g = a.seg[a.nseg++];
-      g.inp = (i == 0) ? A->X : A->Hs[d][i - 1];
-      g.perm = (i == 0) ? S->perm[d] : nullptr;
-      g.ld_inp = (i == 0) ? A->ldx : A->ldh;
-      g.Hcur = A->Hs[d][i];
-      g.Hout = A->Hs[d][i];
-      g.rowptr = S->rowptr[d];
-      g.col = S->col[d];
-      g.eattr = A->use_edge_attr ? S->eattr[d] : nullptr;
-      g.perm_vid = A->nvid > 0 ? S->perm[d] : nullptr;
+      const DagnnPackLayout& L = i == 0 ? lay0 : layL;
       const float* pk = A->packed[d][i];
-      g.w = pk + P.w_off; g.bias = pk + P.bias_off; g.wk = pk + P.wk_off; g.attnc = pk + P.attnc_off; g.vidk = pk + P.vidk_off;
-      g.pos0 = A->lvl_off_host[d][l];
-      g.n_nodes = pend[q].n;
-      g.Din = P.Din; g.Kin = P.Kin;
-      g.level0 = (l == 0);
-      g.tile_begin = tiles;
-      tiles += ceil_div(pend[q].n, BM) * NS;
+      LayP& q = P.lay[d][i];
+      q.Hs = A->Hs[d][i]; q.w = pk + L.w_off; q.bias = pk + L.bias_off; q.wk = pk + L.wk_off; q.attnc = pk + L.attnc_off;
+      q.vidk = pk + L.vidk_off;
     }
-    const size_t smem = smem_for(BM, kin_step, Kh);
-    int rc;
-    if (BM == 64) rc = launch_step<64>(a, tiles, smem, st);
-    else if (BM == 32) rc = launch_step<32>(a, tiles, smem, st);
-    else rc = launch_step<16>(a, tiles, smem, st);
-    if (rc) return rc;
   }
-  return DAGNN_OK;
+  const int Kin_max = layers > 1 ? (lay0.Kin > layL.Kin ? lay0.Kin : layL.Kin) : lay0.Kin;
+  if (smem_for(32, Kin_max, P.Kh, 3) > (size_t)kMaxSmem) return set_err(DAGNN_E_UNSUPPORTED, "sweep: Din=%d too wide", A->Din);
+
+  int dev = 0;
+  DAGNN_CUDA_OK(cudaGetDevice(&dev));
+  static int sm_count[64] = {0};
+  if (dev >= 64) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device ordinal %d", dev);
+  if (sm_count[dev] == 0) {
+    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    int n = 0, coop = 0;
+    DAGNN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    DAGNN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device has no cooperative launch");
+    sm_count[dev] = n;
+  }
+  const int G = sm_count[dev];
+  // shared-memory plan: A tile rows (64 or 32), weight ring depth, resident slice of the weight-stationary path
+  P.allow64 = smem_for(64, Kin_max, P.Kh, 4) <= (size_t)kMaxSmem;
+  P.upc = 0;
+  const int pairs = dirs * layers;
+  const bool no_stat = getenv("DAGNN_NO_STATIONARY") != nullptr;
+  for (int a64 = P.allow64; a64 >= 0 && !P.upc && !no_stat; --a64)
+    for (int upc = 8; upc <= 32; upc *= 2)
+      if (pairs * ceil_div(H, upc) <= G && smem_for(a64 ? 64 : 32, Kin_max, P.Kh, 3, upc) <= (size_t)kMaxSmem) {
+        P.upc = upc; P.SP = ceil_div(H, upc); P.allow64 = a64;
+        break;
+      }
+  P.nsmall = kNSmall;
+  P.ldag = Kin_max + P.Kh;
+  P.Ag = reinterpret_cast<float*>(static_cast<char*>(A->workspace) + 256);
+  P.stages = kMaxStages;
+  while (smem_for(P.allow64 ? 64 : 32, Kin_max, P.Kh, P.stages, P.upc) > (size_t)kMaxSmem) --P.stages;
+  const size_t smem = smem_for(P.allow64 ? 64 : 32, Kin_max, P.Kh, P.stages, P.upc);
+
+  DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 16, st));
+  void* kargs[] = {(void*)&P};
+  DAGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sweep_persistent, dim3(G), dim3(kThreads), kargs, smem, st));
+  return check_launch("k_sweep_persistent");
 }

@@ -11,11 +11,17 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   const int K = L.Kin + L.Kh;
   const int64_t total = (int64_t)L.NS * K * 3 * DAGNN_UNIT_SLICE;
   float* w = packed + L.w_off;
+  // [slice][k-block of 16][kq 4][gate 3][unit 32][k4 4]: a thread (= unit) reads float4 over k, a warp 512 contiguous bytes
+  constexpr int kBlk = DAGNN_K_BLOCK * 3 * DAGNN_UNIT_SLICE;
+  const int nkb = K / DAGNN_K_BLOCK;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(idx % DAGNN_UNIT_SLICE);
-    const int g = (int)((idx / DAGNN_UNIT_SLICE) % 3);
-    const int k = (int)((idx / (3 * DAGNN_UNIT_SLICE)) % K);
-    const int sl = (int)(idx / ((int64_t)3 * DAGNN_UNIT_SLICE * K));
+    const int k4 = (int)(idx % 4);
+    const int u = (int)((idx / 4) % DAGNN_UNIT_SLICE);
+    const int g = (int)((idx / (4 * DAGNN_UNIT_SLICE)) % 3);
+    const int kq = (int)((idx / (12 * DAGNN_UNIT_SLICE)) % (DAGNN_K_BLOCK / 4));
+    const int kb = (int)((idx / kBlk) % nkb);
+    const int sl = (int)(idx / ((int64_t)kBlk * nkb));
+    const int k = kb * DAGNN_K_BLOCK + kq * 4 + k4;
     const int unit = sl * DAGNN_UNIT_SLICE + u;
     float v = 0.f;
     if (unit < L.H) {

@@ -105,17 +105,17 @@ class _DagnnDvaeBase(_DVAEParams):
         self.out_linear = nn.Linear(self.out_hidden_dim, out_dim) if num_layers > 1 else None
         self._packed = rt.PackedParams()
 
-    def build_schedule(self, G) -> rt.Schedule:
+    def build_schedule(self, G, max_levels: int = 256) -> rt.Schedule:
         bi = G.bi_layer_index
         nd = len(self.dirs)
         lv = [bi[d][0] for d in range(nd)]
         ids = [bi[d][1] for d in range(nd)]
         ng = getattr(G, "num_graphs", None)
         ng = int(ng) if ng is not None else int(G.batch[-1].item()) + 1
-        return rt.Schedule.build(G.edge_index, lv, ids, None, G.batch, ng)
+        return rt.Schedule.build(G.edge_index, lv, ids, None, G.batch, ng, max_levels)
 
-    def node_states(self, G, sched=None):
-        sched = sched if sched is not None else self.build_schedule(G)
+    def node_states(self, G, sched=None, max_levels: int = 256):
+        sched = sched if sched is not None else self.build_schedule(G, max_levels)
         cells = [getattr(self, "cells_%d" % d) for d in self.dirs]
         aggrs = [getattr(self, "node_aggr_%d" % d) for d in self.dirs]
         nv = self.num_nodes if self._VID else 0
@@ -129,14 +129,16 @@ class _DagnnDvaeBase(_DVAEParams):
         (forward states) [‖ first node (backward states)] over all layers -> out_linear / hg_unify."""
         _forward_only_guard(self)
         G = G.to(self.get_device())
-        X, Hs, sched = self.node_states(G)
-        H, blocks, col = self.hidden_dim, [], 0
-        for l in range(self.num_layers):
-            blocks.append(dict(src=Hs[0, l], width=H, index_mode=1, dir=0, filter=rt.FILTER_LAST, out_col=col)); col += H
-        if self.bidirectional:
+        def run(max_levels):
+            X, Hs, sched = self.node_states(G, None, max_levels)
+            H, blocks, col = self.hidden_dim, [], 0
             for l in range(self.num_layers):
-                blocks.append(dict(src=Hs[1, l], width=H, index_mode=1, dir=1, filter=rt.FILTER_FIRST, out_col=col)); col += H
-        hcat = rt.readout(sched, blocks, "add", col, X.device)
+                blocks.append(dict(src=Hs[0, l], width=H, index_mode=1, dir=0, filter=rt.FILTER_LAST, out_col=col)); col += H
+            if self.bidirectional:
+                for l in range(self.num_layers):
+                    blocks.append(dict(src=Hs[1, l], width=H, index_mode=1, dir=1, filter=rt.FILTER_FIRST, out_col=col)); col += H
+            return rt.readout(sched, blocks, "add", col, X.device), sched
+        hcat = rt.run_checked(run)
         if self.bidirectional:
             return self.hg_unify(hcat)
         return self.out_linear(hcat) if self.num_layers > 1 else hcat

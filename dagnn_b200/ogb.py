@@ -121,23 +121,24 @@ class DAGNN(nn.Module):
         ng = getattr(G, "num_graphs", None)
         return int(ng) if ng is not None else int(G.batch[-1].item()) + 1
 
-    def build_schedule(self, G) -> rt.Schedule:
+    def build_schedule(self, G, max_levels: int = 256) -> rt.Schedule:
         lv = [G._bi_layer_idx0, G._bi_layer_idx1][:len(self.dirs)]
         ids = [G._bi_layer_index0, G._bi_layer_index1][:len(self.dirs)]
         ea = G.edge_attr if self.w_edge_attr else None
-        return rt.Schedule.build(G.edge_index, lv, ids, ea, G.batch, self._num_graphs(G))
+        return rt.Schedule.build(G.edge_index, lv, ids, ea, G.batch, self._num_graphs(G), max_levels)
 
     def _pack(self, device) -> rt.PackedParams:
         cells = [getattr(self, "cells_%d" % d) for d in self.dirs]
         aggrs = [getattr(self, "node_aggr_%d" % d) for d in self.dirs]
         return self._packed.update(cells, aggrs, self.emb_dim, self.hidden_dim, 0, self.w_edge_attr, device)
 
-    def node_states(self, G, sched=None):
-        """encoder + level sweep: returns (X [N,D], Hs [dirs, layers, N, ldh] in position order, schedule)."""
+    def node_states(self, G, sched=None, max_levels: int = 256):
+        """encoder + level sweep: returns (X [N,D], Hs [dirs, layers, N, ldh] in position order, schedule).
+        Asynchronous and unchecked: call `sched.finalize()` (or go through forward_readout) to validate."""
         X = self.encoder(G.x, G.node_depth.view(-1, ))
         if X.shape[1] != self.emb_dim:
             raise ValueError("encoder produced width %d, emb_dim is %d" % (X.shape[1], self.emb_dim))
-        sched = sched if sched is not None else self.build_schedule(G)
+        sched = sched if sched is not None else self.build_schedule(G, max_levels)
         packed = self._pack(X.device)
         Hs = rt.sweep(sched, X, packed, self.emb_dim, self.hidden_dim, self.num_layers, 0, self.w_edge_attr)
         return X, Hs, sched
@@ -165,8 +166,10 @@ class DAGNN(nn.Module):
 
     def forward_readout(self, G):
         """The north-star hot path: encoder -> schedule -> level sweeps (both directions) -> pooled readout."""
-        X, Hs, sched = self.node_states(G)
-        return self.readout(G, X, Hs, sched)
+        def run(max_levels):
+            X, Hs, sched = self.node_states(G, None, max_levels)
+            return self.readout(G, X, Hs, sched), sched
+        return rt.run_checked(run)
 
     def forward(self, G):
         _forward_only_guard(self)

@@ -51,14 +51,19 @@ def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, m
 
 
 class Schedule(object):
-    """Level-sorted node order + in-edge CSR per direction, built on the device (schedule.cu)."""
+    """Level-sorted node order + in-edge CSR per direction, built on the device (schedule.cu).
+
+    `build` only enqueues kernels; nothing in a forward waits for the host. `finalize()` brings the 8-int summary and
+    the level offsets to the host (one small D2H + sync): the module calls it once at the END of a forward to check the
+    status word, tests call it to inspect the arrays."""
 
     def __init__(self):
         self.c = DagnnSchedule()
         self.buf = None
         self.host_head = None
-        self.lvl_off_host: List[np.ndarray] = []
-        self.num_levels: List[int] = []
+        self._final = False
+        self._lvl_off_host: List[np.ndarray] = []
+        self._num_levels: List[int] = []
         self._keep = []
 
     @staticmethod
@@ -77,63 +82,80 @@ class Schedule(object):
         if batch is not None:
             batch = _req_cuda(batch, "batch", torch.int64)
         N, E, B = int(levels[0].shape[0]), int(edge_index.shape[1]), int(num_graphs)
-        while True:
-            s = Schedule()
-            ML = int(max_levels)
-            head = 8 + dirs * (ML + 1)
-            sizes = [("head", head)]
-            for d in range(dirs):
-                sizes += [("perm%d" % d, N), ("pos%d" % d, N), ("rowptr%d" % d, N + 1), ("col%d" % d, E), ("eid%d" % d, E)]
-                if edge_attr is not None:
-                    sizes.append(("eattr%d" % d, 2 * E))
-            sizes.append(("gptr", B + 1))
-            offs, tot = {}, 0
-            for k, n in sizes:
-                offs[k] = tot
-                tot += _align(max(n, 1))
-            ws_bytes = lib().dagnn_schedule_workspace_bytes(N, E, ML)
-            buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
-            s.buf = buf
-            view = lambda k, n: buf[offs[k]: offs[k] + n]
-            c = s.c
-            c.N, c.E, c.B, c.dirs, c.max_levels = N, E, B, dirs, ML
-            s.summary = view("head", 8)
-            c.summary = s.summary.data_ptr()
-            s.perm, s.pos, s.lvl_off, s.rowptr, s.col, s.eid, s.eattr = [], [], [], [], [], [], []
-            for d in range(dirs):
-                s.perm.append(view("perm%d" % d, N)); s.pos.append(view("pos%d" % d, N))
-                s.lvl_off.append(buf[offs["head"] + 8 + d * (ML + 1): offs["head"] + 8 + (d + 1) * (ML + 1)])
-                s.rowptr.append(view("rowptr%d" % d, N + 1)); s.col.append(view("col%d" % d, E)); s.eid.append(view("eid%d" % d, E))
-                s.eattr.append(view("eattr%d" % d, 2 * E).view(torch.float32).view(E, 2) if edge_attr is not None else None)
-                c.perm[d], c.pos[d], c.lvl_off[d] = s.perm[d].data_ptr(), s.pos[d].data_ptr(), s.lvl_off[d].data_ptr()
-                c.rowptr[d], c.col[d], c.eid[d] = s.rowptr[d].data_ptr(), s.col[d].data_ptr(), s.eid[d].data_ptr()
-                c.eattr[d] = s.eattr[d].data_ptr() if edge_attr is not None else None
-            s.gptr = view("gptr", B + 1)
-            c.gptr = s.gptr.data_ptr()
-            ws = buf[tot:]
-            check(lib().dagnn_schedule_build(_ptr(edge_index), _ptr(levels[0]), _ptr(levels[1]) if dirs == 2 else None,
-                                             _ptr(node_ids[0]), _ptr(node_ids[1]) if dirs == 2 else None,
-                                             _ptr(edge_attr), _ptr(batch), C.byref(c), ws.data_ptr(), ws_bytes, _stream()),
-                  "dagnn_schedule_build")
-            # the one host<->device round trip of a forward: 8 + dirs*(ML+1) ints (the reference syncs at
-            # dagnn.py:137 and once per node at :155)
-            host = torch.empty(head, dtype=torch.int32, pin_memory=True)
-            host.copy_(buf[:head], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            hn = host.numpy()
-            status = int(hn[2])
-            if status == 1 and ML < (1 << 22):
-                max_levels = ML * 8
-                continue
-            if status != 0:
-                raise _lib.DagnnError("schedule build: status %d (1: level >= max_levels, 2: node id / edge endpoint / "
-                                      "batch vector out of range)" % status)
-            s.host_head = host
-            s.num_levels = [int(hn[d]) for d in range(dirs)]
-            s.lvl_off_host = [hn[8 + d * (ML + 1): 8 + (d + 1) * (ML + 1)] for d in range(dirs)]
-            s._keep = [edge_index, levels, node_ids, edge_attr, batch]
-            s.has_edge_attr = edge_attr is not None
-            return s
+        s = Schedule()
+        ML = int(max_levels)
+        head = 8 + dirs * (ML + 1)
+        sizes = [("head", head)]
+        for d in range(dirs):
+            sizes += [("perm%d" % d, N), ("pos%d" % d, N), ("rowptr%d" % d, N + 1), ("col%d" % d, E), ("eid%d" % d, E)]
+            if edge_attr is not None:
+                sizes.append(("eattr%d" % d, 2 * E))
+        sizes.append(("gptr", B + 1))
+        offs, tot = {}, 0
+        for k, n in sizes:
+            offs[k] = tot
+            tot += _align(max(n, 1))
+        ws_bytes = lib().dagnn_schedule_workspace_bytes(N, E, ML)
+        buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
+        s.buf, s.head_len, s.max_levels = buf, head, ML
+        view = lambda k, n: buf[offs[k]: offs[k] + n]
+        c = s.c
+        c.N, c.E, c.B, c.dirs, c.max_levels = N, E, B, dirs, ML
+        s.summary = view("head", 8)
+        c.summary = s.summary.data_ptr()
+        s.perm, s.pos, s.lvl_off, s.rowptr, s.col, s.eid, s.eattr = [], [], [], [], [], [], []
+        for d in range(dirs):
+            s.perm.append(view("perm%d" % d, N)); s.pos.append(view("pos%d" % d, N))
+            s.lvl_off.append(buf[offs["head"] + 8 + d * (ML + 1): offs["head"] + 8 + (d + 1) * (ML + 1)])
+            s.rowptr.append(view("rowptr%d" % d, N + 1)); s.col.append(view("col%d" % d, E)); s.eid.append(view("eid%d" % d, E))
+            s.eattr.append(view("eattr%d" % d, 2 * E).view(torch.float32).view(E, 2) if edge_attr is not None else None)
+            c.perm[d], c.pos[d], c.lvl_off[d] = s.perm[d].data_ptr(), s.pos[d].data_ptr(), s.lvl_off[d].data_ptr()
+            c.rowptr[d], c.col[d], c.eid[d] = s.rowptr[d].data_ptr(), s.col[d].data_ptr(), s.eid[d].data_ptr()
+            c.eattr[d] = s.eattr[d].data_ptr() if edge_attr is not None else None
+        s.gptr = view("gptr", B + 1)
+        c.gptr = s.gptr.data_ptr()
+        ws = buf[tot:]
+        check(lib().dagnn_schedule_build(_ptr(edge_index), _ptr(levels[0]), _ptr(levels[1]) if dirs == 2 else None,
+                                         _ptr(node_ids[0]), _ptr(node_ids[1]) if dirs == 2 else None,
+                                         _ptr(edge_attr), _ptr(batch), C.byref(c), ws.data_ptr(), ws_bytes, _stream()),
+              "dagnn_schedule_build")
+        s._keep = [edge_index, levels, node_ids, edge_attr, batch]
+        s.has_edge_attr = edge_attr is not None
+        return s
+
+    def finalize(self) -> "Schedule":
+        """D2H of the summary + level offsets, then validate. status 1 (a level >= max_levels) raises
+        `ScheduleOverflow` so the caller can rebuild with a larger table."""
+        if self._final:
+            return self
+        host = torch.empty(self.head_len, dtype=torch.int32, pin_memory=True)
+        host.copy_(self.buf[: self.head_len], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hn = host.numpy()
+        status = int(hn[2])
+        if status == 1:
+            raise ScheduleOverflow(self.max_levels)
+        if status != 0:
+            raise _lib.DagnnError("schedule build: status %d (2: node id / edge endpoint / batch vector out of range)" % status)
+        dirs, ML = self.c.dirs, self.max_levels
+        self.host_head = host
+        self._num_levels = [int(hn[d]) for d in range(dirs)]
+        self._lvl_off_host = [hn[8 + d * (ML + 1): 8 + (d + 1) * (ML + 1)] for d in range(dirs)]
+        if self._num_levels[0] < 1:
+            raise _lib.DagnnError("empty batch")
+        if dirs == 2 and self._num_levels[1] > self._num_levels[0]:
+            raise _lib.DagnnError("direction 1 has more levels (%d) than direction 0 (%d): level arrays are not the "
+                                  "longest-path levels of one DAG" % (self._num_levels[1], self._num_levels[0]))
+        self._final = True
+        return self
+
+    @property
+    def num_levels(self) -> List[int]:
+        return self.finalize()._num_levels
+
+    @property
+    def lvl_off_host(self) -> List[np.ndarray]:
+        return self.finalize()._lvl_off_host
 
     # ---- views used by tests (bit-exact parity of the integer pre-pass) ----
     def level_nodes(self, d: int, l: int) -> torch.Tensor:
@@ -145,6 +167,27 @@ class Schedule(object):
         rp = self.rowptr[d]
         e0, e1 = int(rp[a]), int(rp[b])
         return self.eid[d][e0:e1].long()
+
+
+class ScheduleOverflow(_lib.DagnnError):
+    def __init__(self, max_levels):
+        super().__init__("a level index >= max_levels=%d" % max_levels)
+        self.max_levels = max_levels
+
+
+def run_checked(fn, max_levels: int = 256):
+    """fn(max_levels) -> (result, schedule). Runs the whole forward asynchronously, then checks the schedule status
+    once at the end (the single host<->device round trip of a forward; the reference syncs at dagnn.py:137 and once per
+    node at :155). Rebuilds with a larger level table if the batch is deeper than max_levels."""
+    while True:
+        res, sched = fn(max_levels)
+        try:
+            sched.finalize()
+            return res
+        except ScheduleOverflow:
+            if max_levels >= (1 << 22):
+                raise
+            max_levels *= 8
 
 
 class PackedParams(object):
@@ -202,30 +245,46 @@ class PackedParams(object):
         return self
 
 
+_WS = {}
+
+
+def _sweep_workspace(device, dirs, layers, Din, H) -> torch.Tensor:
+    need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H))
+    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
+    w = _WS.get(key)
+    if w is None or w.numel() * 4 < need:
+        w = torch.zeros((need + 3) // 4, device=device, dtype=torch.int32)
+        _WS[key] = w
+    return w
+
+
 def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: int, num_layers: int, nvid: int = 0,
-          use_edge_attr: bool = False) -> torch.Tensor:
-    """The level sweep. Returns Hs fp32 [dirs, layers, N, ldh] in POSITION order (row p = node perm[d][p])."""
+          use_edge_attr: bool = False, trace_steps: int = 0):
+    """The level sweep (one persistent kernel). Returns Hs fp32 [dirs, layers, N, ldh] in POSITION order
+    (row p = node perm[d][p]). Asynchronous: level offsets / level count are read on the device."""
     X = _req_cuda(X, "X", torch.float32)
     dirs, N = sched.c.dirs, sched.c.N
-    if sched.num_levels[0] < 1:
-        raise _lib.DagnnError("empty batch")
-    if dirs == 2 and sched.num_levels[1] > sched.num_levels[0]:
-        raise _lib.DagnnError("direction 1 has more levels (%d) than direction 0 (%d): level arrays are not the "
-                              "longest-path levels of one DAG" % (sched.num_levels[1], sched.num_levels[0]))
     ldh = (H + 3) // 4 * 4
     Hs = torch.empty(dirs, num_layers, N, ldh, device=X.device, dtype=torch.float32)
+    ws = _sweep_workspace(X.device, dirs, num_layers, Din, H)
     a = DagnnSweepArgs()
     a.sched = C.pointer(sched.c)
     for d in range(dirs):
-        a.lvl_off_host[d] = sched.lvl_off_host[d].ctypes.data_as(C.POINTER(C.c_int32))
         for i in range(num_layers):
             a.Hs[d][i] = Hs[d, i].data_ptr()
             a.packed[d][i] = packed.blobs[d][i].data_ptr()
-    a.num_levels, a.num_layers = sched.num_levels[0], num_layers
+    a.num_layers = num_layers
     a.Din, a.H, a.nvid = Din, H, nvid
     a.X, a.ldx, a.ldh = X.data_ptr(), X.stride(0), ldh
     a.use_edge_attr = 1 if use_edge_attr else 0
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    trace = None
+    if trace_steps > 0:     # profiling: per (step, CTA) clock64 stamps, see include/dagnn_b200.h
+        trace = torch.zeros(int(lib().dagnn_sweep_trace_bytes(trace_steps)) // 8, device=X.device, dtype=torch.int64)
+        a.trace = trace.data_ptr()
     check(lib().dagnn_sweep_forward_f32(C.byref(a), _stream()), "dagnn_sweep_forward_f32")
+    if trace is not None:
+        return Hs, trace.view(trace_steps, 256, 8)
     return Hs
 
 

@@ -27,10 +27,10 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 1
+#define DAGNN_ABI_VERSION 2
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
-#define DAGNN_UNIT_SLICE 128        /* hidden units per weight slice of the packed layout        */
+#define DAGNN_UNIT_SLICE 32         /* hidden units per weight slice of the packed layout        */
 #define DAGNN_K_BLOCK 16            /* K granularity of the packed layout (rows per stage)       */
 #define DAGNN_MAX_READOUT_BLOCKS 20 /* column blocks of one readout call                         */
 
@@ -101,9 +101,9 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
  * The query part of attn_lin (first Dq columns), attn_lin.bias and edge_encoder.bias add the same constant
  * to every in-edge score of a node and cancel in the softmax, so they are not packed.
  * Layout of `packed` (floats), all offsets from dagnn_pack_layout():
- *   w     [NS][Kin+Kh][3][128]  NS=ceil(H/128); Kin=roundup(Din,16); Kh=roundup(H,16)
- *   bias  [4][NS*128]           b_r=b_ir+b_hr, b_z=b_iz+b_hz, b_in, b_hn
- *   wk    [NS*128]              key weights on the hidden state
+ *   w     [NS][Kin+Kh][3][32]   NS=ceil(H/32); Kin=roundup(Din,16); Kh=roundup(H,16)
+ *   bias  [4][NS*32]            b_r=b_ir+b_hr, b_z=b_iz+b_hz, b_in, b_hn
+ *   wk    [NS*32]               key weights on the hidden state
  *   attnc [4]                   {wk·W_e[:,0], wk·W_e[:,1], 0, 0}
  *   vidk  [nvid]                key weights on the one-hot vertex id (D-VAE NA), nvid may be 0
  * --------------------------------------------------------------------------------------------------------- */
@@ -125,14 +125,14 @@ int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const 
  *   inp_v = GRUCell_{d,i}(inp_v, m_v);  H[d][i][v] = inp_v          (inp_v starts as X[v])
  * replaces dagnn.py:144-182 incl. AttnConv (:362-373), PyG propagate/softmax/scatter-add, nn.GRUCell (:181) and
  * the index_put at :182; D-VAE variants dvae/dagnn.py:109-145, dvae/dagnn_bn.py:108-136.
- * One fused kernel launch per wavefront step s = level + layer (all (d, layer) pairs of the step in one
- * grid). States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
- * `lvl_off_host[d]` is a host copy of sched->lvl_off[d][0..num_levels] (the launcher sizes grids from it).
+ * ONE persistent cooperative kernel runs the whole sweep: wavefront step s = level + layer processes all (d, layer)
+ * pairs of the step, tiles dealt to one CTA per SM, grid barrier between steps. Level offsets and the level count
+ * (reference: max level of direction 0, + 1 — dagnn.py:137) are read from the schedule's DEVICE arrays, so a forward
+ * needs no host synchronisation. If sched->summary[2] != 0 (bad input) the kernel does nothing; the caller checks the
+ * status. States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnSweepArgs {
   const DagnnSchedule* sched;
-  const int32_t* lvl_off_host[DAGNN_MAX_DIRS];
-  int32_t num_levels;                  /* levels swept (reference: max level of direction 0, + 1)  */
   int32_t num_layers;
   int32_t Din, H, nvid;                /* input width, hidden width, #vertex-id columns (0 = none) */
   const float* X;                      /* [N, ldx] node features in NODE order                      */
@@ -141,8 +141,15 @@ typedef struct DagnnSweepArgs {
   int64_t ldh;                         /* >= roundup(H,4), multiple of 4                            */
   const float* packed[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];     /* dagnn_pack_params_f32 outputs       */
   int32_t use_edge_attr;               /* 1: add the edge-type score term (sched->eattr must exist) */
+  void* workspace;                     /* device scratch, dagnn_sweep_workspace_bytes(), 256-byte aligned */
+  size_t workspace_bytes;
+  void* trace;                         /* optional profiling buffer (NULL = off): int64 [steps][grid<=256][8] clock64 stamps:
+                                          0 step begin, 1 first tile gathered, 2 first tile GEMM done, 3 first tile stored,
+                                          4 all tiles done, 5 barrier passed, 6 #tiles of this CTA, 7 big-tile step        */
 } DagnnSweepArgs;
 
+size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H);
+size_t dagnn_sweep_trace_bytes(int32_t max_steps);
 int dagnn_sweep_forward_f32(const DagnnSweepArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
