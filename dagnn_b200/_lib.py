@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdagnn_sm100.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "schedule.cu", "embed_readout.cu", "pack.cu", "level_sweep.cu"]
+SOURCES = ["abi.cu", "schedule.cu", "embed_readout.cu", "pack.cu", "level_sweep.cu", "tc_selftest.cu"]
+HEADERS = ["common.cuh", "tc.cuh"]
 
 MAX_LAYERS = 8
 MAX_DIRS = 2
@@ -74,6 +75,7 @@ EXPORTS = {
     "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
+    "dagnn_tc_selftest_f32": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),
     "dagnn_states_to_node_order_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.c_int32, vp, C.c_int64, C.c_int32, vp,
@@ -93,8 +95,7 @@ def nvcc_command(out_path: str = LIB_PATH):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into dagnn_b200/libdagnn_sm100.so (in-tree)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
-                                                        os.path.join(ROOT, "include", "dagnn_b200.h")]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "dagnn_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     cmd = nvcc_command()

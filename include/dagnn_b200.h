@@ -175,6 +175,10 @@ typedef struct DagnnReadoutBlock {
 int dagnn_readout_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* blocks, int32_t nblocks, int32_t pool,
                       float* out, int64_t ldo, void* stream);
 
+/* Diagnostic: C[M,N] = A[M,K] * B[N,K]^T (fp32 row-major) through the same tcgen05 3xTF32 building blocks the level
+ * kernel uses (K-major SWIZZLE_128B operand tiles, TMEM accumulators). N % 16 == 0, 16 <= N <= 256, K % 32 == 0. */
+int dagnn_tc_selftest_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* Un-permute states for inspection / tests: dst[v,:] = src[pos[dir][v],:]  (fp32 [N,H]) */
 int dagnn_states_to_node_order_f32(const DagnnSchedule* sched, int32_t dir, const float* src, int64_t lds,
                                    int32_t H, float* dst, int64_t ldd, void* stream);
