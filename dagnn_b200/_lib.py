@@ -37,8 +37,9 @@ class DagnnSchedule(C.Structure):
 class DagnnPackLayout(C.Structure):
     _fields_ = [
         ("Din", C.c_int32), ("H", C.c_int32), ("Kin", C.c_int32), ("Kh", C.c_int32), ("NS", C.c_int32), ("nvid", C.c_int32),
+        ("Kin32", C.c_int32), ("Kh32", C.c_int32), ("UT", C.c_int32), ("reserved", C.c_int32),
         ("w_off", C.c_int64), ("bias_off", C.c_int64), ("wk_off", C.c_int64), ("attnc_off", C.c_int64),
-        ("vidk_off", C.c_int64), ("total_floats", C.c_int64),
+        ("vidk_off", C.c_int64), ("tc_off", C.c_int64), ("total_floats", C.c_int64),
     ]
 
 

@@ -20,6 +20,7 @@
 // States written in one step are read in later steps by OTHER CTAs: all state reads use ld.global.cg (L2), the
 // barrier is the cooperative-groups pattern (bar.sync; fence; atomic; spin on ld.acquire; bar.sync).
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace dagnn {
 
@@ -29,8 +30,11 @@ constexpr int kThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kWSliceFloats = BK * 3 * US;      // 1536 floats = one k-block of one 32-unit slice
 constexpr int kWSliceBytes = kWSliceFloats * 4; // 6144
-constexpr int kWStageFloats = 2 * kWSliceFloats; // a ring stage holds up to two slices (64-unit tiles)
-constexpr int kBarBytes = 128;
+constexpr int kWStageFloats = kWSliceFloats;     // one ring stage = one k-block of one slice
+constexpr int kBarBytes = 128;                  // 8 ring barriers + tensor-core path: full_b[2], mma_done[2]
+constexpr int kTcStageBytes = 2 * 128 * tc::ROW_BYTES + 2 * 192 * tc::ROW_BYTES;   // A hi/lo + B hi/lo = 80 KB
+constexpr int kTcBytes = 2 * kTcStageBytes + 1024;                                 // two stages + row-pointer cache
+constexpr int kTcCols = 256;                    // TMEM columns: [n_in | r | z | n_hid] x 64 units
 constexpr int kMaxSmem = 232448;                // 227 KB opt-in limit per CTA on sm_100
 
 struct DirP {
@@ -47,11 +51,16 @@ struct LayP {
   const float* wk;      // [NS*US]
   const float* attnc;   // [4]
   const float* vidk;    // [nvid]
+  const float* wtc;     // tensor-core image of the weights (pack.cu k_pack_tc)
+  float* alpha;         // [E] scratch: softmax weight of every in-edge (CSR order) of the rows a TC tile owns
+  float* skp;           // [N][nsk] partial key scores wk . h over 8-unit groups, written with every state row
 };
 struct SweepP {
   int dirs, layers, H, Hq, Kh, NS, nvid, use_ea;
   int Din0, Kin0;       // layer 0 input width and its padded K; layers > 0 take H / Kh
   int allow64, stages;
+  int tc_on, nsk, nskv, nci0, ncih, UT, ubytes, pad2_;   // tensor-core path: on/off, key-score partials per row, 32-k chunks of the layer-0 input /
+                        // hidden part, 64-unit tiles, bytes of the union smem region
   int upc, SP, nsmall, ldag;   // weight-stationary path: units per CTA (0 = off), CTAs per (d,i) pair, row threshold, scratch ld
   float* Ag;            // [pairs][nsmall][ldag] gathered A rows of the small segments of the current step
   long long ldh, ldx;
@@ -138,6 +147,12 @@ struct TileCtx {
   float* Ws;
   float* As;
   long long* tr; // trace slot of the current (step, CTA) while its first tile runs, else nullptr
+  unsigned char* U;  // 1024-aligned union region: tensor-core stages | FFMA ring + A tile
+  uint64_t* full_b;  // [2] B chunk landed
+  uint64_t* mma_done; // [2] MMAs reading a stage finished
+  int* rp;           // [130] row pointers of the current TC tile
+  uint32_t tmem;     // TMEM base address (kTcCols columns)
+  uint32_t cc;       // cumulative TC chunk count (stage = cc & 1)
   uint32_t it;   // cumulative weight-ring iteration count of this CTA (stage = it % kStages, parity = (it / kStages) & 1)
 };
 
@@ -248,6 +263,7 @@ __device__ __forceinline__ void process_tile(const SweepP& P, int d, int i, bool
                kWSliceBytes, bar);
   };
 
+  tc::fence_async_smem();
   __syncthreads();   // previous tile: ring drained, A tile and epilogue reads done
   if (tid == 0) {
     const int npre = min(S - 1, nkb);
@@ -301,23 +317,30 @@ __device__ __forceinline__ void process_tile(const SweepP& P, int d, int i, bool
   }
   T.it += nkb;
 
-  // ---------------- phase 3: GRU pointwise + store ----------------
+  // ---------------- phase 3: GRU pointwise + store (+ key-score partials over 8-unit groups) ----------------
   const int u = (sl0 + wu) * US + lane;
-  if (active && u < Hq) {
-    const int HP = P.NS * US;
-    const float br = __ldg(Lp.bias + u), bz = __ldg(Lp.bias + HP + u), bi = __ldg(Lp.bias + 2 * HP + u),
-                bh = __ldg(Lp.bias + 3 * HP + u);
+  const bool uok = active && u < Hq;
+  const int HP = P.NS * US;
+  const float br = uok ? __ldg(Lp.bias + u) : 0.f, bz = uok ? __ldg(Lp.bias + HP + u) : 0.f,
+              bi = uok ? __ldg(Lp.bias + 2 * HP + u) : 0.f, bh = uok ? __ldg(Lp.bias + 3 * HP + u) : 0.f;
+  const float wku = uok ? __ldg(Lp.wk + u) : 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int m = row0 + r;
-      if (m < nvalid) {
-        const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
-        const float rg = sigmoidf_(acc_r[r] + br);
-        const float zg = sigmoidf_(acc_z[r] + bz);
-        const float ng = tanhf(acc_n[r] + bi + rg * (acc_h[r] + bh));
-        Lp.Hs[(size_t)(p0 + m) * P.ldh + u] = ng + zg * (hp - ng);
-      }
+  for (int r = 0; r < R; ++r) {
+    const int m = row0 + r;
+    float o = 0.f;
+    if (uok && m < nvalid) {
+      const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
+      const float rg = sigmoidf_(acc_r[r] + br);
+      const float zg = sigmoidf_(acc_z[r] + bz);
+      const float ng = tanhf(acc_n[r] + bi + rg * (acc_h[r] + bh));
+      o = ng + zg * (hp - ng);
+      Lp.Hs[(size_t)(p0 + m) * P.ldh + u] = o;
     }
+    float pk = o * wku;
+    pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+    pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+    pk += __shfl_xor_sync(0xffffffffu, pk, 4);
+    if (active && (lane & 7) == 0 && m < nvalid && (u >> 3) < P.nsk) Lp.skp[(size_t)(p0 + m) * P.nsk + (u >> 3)] = pk;
   }
 }
 
@@ -355,8 +378,9 @@ __device__ __forceinline__ void stationary_chunk(const SweepP& P, const LayP& Lp
 #pragma unroll
     for (int j = 0; j < UPT; ++j) acc_r[t][j] = acc_z[t][j] = acc_n[t][j] = acc_h[t][j] = 0.f;
   const float* A0 = As + slot * ldA;
-  if (slot < rows) {      // rows beyond the chunk: whole quarter-warps idle
-#pragma unroll 2
+  const bool live = slot < rows;      // rows beyond the chunk: whole quarter-warps idle
+  if (live) {
+#pragma unroll 4
     for (int kq = 0; kq < nkq; ++kq) {
       float4 a[T];
 #pragma unroll
@@ -375,25 +399,33 @@ __device__ __forceinline__ void stationary_chunk(const SweepP& P, const LayP& Lp
         }
       }
     }
-    const int HP = P.NS * US;
+  }
+  const int HP = P.NS * US;
 #pragma unroll
-    for (int j = 0; j < UPT; ++j) {
-      const int u = unit0 + u8 + 8 * j;
-      if (u < P.Hq) {
-        const float br = __ldg(Lp.bias + u), bz = __ldg(Lp.bias + HP + u), bi = __ldg(Lp.bias + 2 * HP + u),
-                    bh = __ldg(Lp.bias + 3 * HP + u);
+  for (int j = 0; j < UPT; ++j) {
+    const int u = unit0 + u8 + 8 * j;
+    const bool uok = live && u < P.Hq;
+    const float br = uok ? __ldg(Lp.bias + u) : 0.f, bz = uok ? __ldg(Lp.bias + HP + u) : 0.f,
+                bi = uok ? __ldg(Lp.bias + 2 * HP + u) : 0.f, bh = uok ? __ldg(Lp.bias + 3 * HP + u) : 0.f;
+    const float wku = uok ? __ldg(Lp.wk + u) : 0.f;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int m = slot + 32 * t;
-          if (m < rows) {
-            const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
-            const float rg = sigmoidf_(acc_r[t][j] + br);
-            const float zg = sigmoidf_(acc_z[t][j] + bz);
-            const float ng = tanhf(acc_n[t][j] + bi + rg * (acc_h[t][j] + bh));
-            Lp.Hs[(size_t)(prow0 + m) * P.ldh + u] = ng + zg * (hp - ng);
-          }
-        }
+    for (int t = 0; t < T; ++t) {
+      const int m = slot + 32 * t;
+      float o = 0.f;
+      if (uok && m < rows) {
+        const float hp = level0 ? 0.f : As[m * ldA + Kin + u];
+        const float rg = sigmoidf_(acc_r[t][j] + br);
+        const float zg = sigmoidf_(acc_z[t][j] + bz);
+        const float ng = tanhf(acc_n[t][j] + bi + rg * (acc_h[t][j] + bh));
+        o = ng + zg * (hp - ng);
+        Lp.Hs[(size_t)(prow0 + m) * P.ldh + u] = o;
       }
+      float pk = o * wku;               // the 8 lanes of a row slot hold 8 consecutive units: one key-score partial
+      pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+      pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+      pk += __shfl_xor_sync(0xffffffffu, pk, 4);
+      const int part = (unit0 + 8 * j) >> 3;
+      if (u8 == 0 && live && m < rows && part < P.nsk) Lp.skp[(size_t)(prow0 + m) * P.nsk + part] = pk;
     }
   }
 }
@@ -419,6 +451,227 @@ __device__ __forceinline__ void stationary_segment(const SweepP& P, int q, int s
     __syncthreads();
     if (rows > 32) stationary_chunk<2, UPT>(P, Lp, Wres, As, ldA, Kin, level0, rows, pos0 + c0, slot * P.upc);
     else stationary_chunk<1, UPT>(P, Lp, Wres, As, ldA, Kin, level0, rows, pos0 + c0, slot * P.upc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core path for BIG segments: tile = 128 rows x 64 hidden units, gate GEMM on tcgen05 in 3xTF32 (tc.cuh).
+//   pre-phase : one thread per row turns the in-edge scores into softmax weights alpha_e. Scores are scalar gathers:
+//               s_e = sum_j skp[nbr][j] (+ edge-type / vertex-id terms) — every producer of a state row also writes the
+//               partial key scores wk . h over 8-unit groups (separable attention score).
+//   main loop : per 32-wide k chunk, all threads build the A chunk [128, 32] (input rows, or m_v = sum_e alpha_e h_e
+//               for that k range) as tf32 hi/lo tiles in the swizzled layout while the previous chunk's MMAs run; the
+//               weight chunk arrives as one 48 KB bulk copy of the pre-swizzled hi/lo image; thread 0 issues
+//               4 k-steps x 3 products of tcgen05.mma (M=128; N=192 input part, N=128+64 hidden part) into TMEM.
+//   epilogue  : tcgen05.ld of [n_in | r | z | n_hid], gates in registers, state row + key-score partials stored.
+// Two-stage ring; `cc` counts chunks across tiles so mbarrier parities stay consistent.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void process_tile_tc(const SweepP& P, int d, int i, bool level0, int pos0, int p0, int nvalid, int ut,
+                                                TileCtx& T) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DirP& D = P.dir[d];
+  const LayP& Lp = P.lay[d][i];
+  const int Din = (i == 0) ? P.Din0 : P.H;
+  const int nci = (i == 0) ? P.nci0 : P.ncih;
+  const int nch_full = P.ncih;
+  const int nchunks = nci + (level0 ? 0 : nch_full);
+  const float* wimg = Lp.wtc + (size_t)ut * (nci + nch_full) * 2 * (192 * 32);
+  const float* inp = (i == 0) ? P.X : P.lay[d][i - 1].Hs;
+  const long long ld_inp = (i == 0) ? P.ldx : P.ldh;
+  const bool vec_in = (i > 0) || ((P.ldx & 3) == 0 && (Din & 3) == 0 && ((uintptr_t)P.X & 15) == 0);
+  const float* Hcur = Lp.Hs;
+  const long long ldh = P.ldh;
+  const int Hq = P.Hq;
+  int* rp = T.rp;
+
+  auto stage_ptr = [&](uint32_t s) { return T.U + (size_t)s * kTcStageBytes; };
+  auto issue_B = [&](uint32_t ccur, int c) {          // thread 0: weight chunk c -> stage ccur & 1
+    const uint32_t s = ccur & 1u;
+    const uint32_t bar = smem_u32(&T.full_b[s]);
+    mbar_expect_tx(bar, 2 * 192 * tc::ROW_BYTES);
+    bulk_g2s(smem_u32(stage_ptr(s) + 2 * 128 * tc::ROW_BYTES), wimg + (size_t)c * 2 * (192 * 32), 2 * 192 * tc::ROW_BYTES, bar);
+  };
+
+  tc::fence_async_smem();   // generic smem traffic of the previous work item before async-proxy writes to the same bytes
+  __syncthreads();          // previous tile: operand stages, row-pointer cache and TMEM reads are done
+  if (tid == 0) issue_B(T.cc, 0);
+  for (int t = tid; t <= nvalid; t += kThreads) rp[t] = D.rowptr[p0 + t];
+  __syncthreads();
+
+  // ---------------- pre-phase: softmax weights of every in-edge of the tile's rows ----------------
+  // (only FINAL weights are stored: the CTAs of the other unit tiles of these rows write the same values concurrently)
+  if (!level0 && tid < nvalid) {
+    const int e0 = rp[tid], e1 = rp[tid + 1];
+    const bool use_ea = P.use_ea && D.eattr != nullptr;
+    const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
+    auto score = [&](int e, bool& valid) {
+      const int sp = D.col[e];
+      valid = sp < pos0;                             // predecessor state exists (earlier level), else a zero row
+      float sc = 0.f;
+      if (valid) {
+        const float* kp = Lp.skp + (size_t)sp * P.nsk;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int j = 0;
+        for (; j + 4 <= P.nskv; j += 4) {
+          const float4 v = ldcg4(kp + j);
+          a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+        }
+        for (; j < P.nskv; ++j) a4.x += __ldcg(kp + j);
+        sc = (a4.x + a4.y) + (a4.z + a4.w);
+      }
+      if (use_ea) {
+        const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
+        sc += ca0 * ea.x + ca1 * ea.y;
+      }
+      if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
+      return sc;
+    };
+    float mx = -INFINITY, sum = 0.f;
+    bool valid;
+    for (int e = e0; e < e1; ++e) {
+      const float sc = score(e, valid);
+      const float mnew = fmaxf(mx, sc);
+      sum = sum * expf(mx - mnew) + expf(sc - mnew);
+      mx = mnew;
+    }
+    const float inv = 1.f / (sum + 1e-16f);
+    for (int e = e0; e < e1; ++e) {
+      const float sc = score(e, valid);
+      Lp.alpha[e] = valid ? expf(sc - mx) * inv : 0.f;   // a not-yet-computed predecessor keeps its softmax mass, adds a zero row
+    }
+  }
+  __syncthreads();
+
+  // ---------------- main loop over k chunks ----------------
+  const uint32_t idesc192 = tc::instr_desc_tf32(128, 192), idesc128 = tc::instr_desc_tf32(128, 128),
+                 idesc64 = tc::instr_desc_tf32(128, 64);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t ccur = T.cc + (uint32_t)c;
+    const uint32_t s = ccur & 1u;
+    if (ccur >= 2) mbar_wait(smem_u32(&T.mma_done[s]), ((ccur - 2) >> 1) & 1u);   // MMAs that read this stage are done
+    unsigned char* A_hi = stage_ptr(s);
+    unsigned char* A_lo = A_hi + 128 * tc::ROW_BYTES;
+    if (c < nci) {
+      const int k0 = c * tc::KC;
+      for (int it = tid; it < 128 * 8; it += kThreads) {
+        const int r = it >> 3, c4 = it & 7, k = k0 + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nvalid && k < Din) {
+          const float* src = inp + (size_t)(i == 0 ? D.perm[p0 + r] : p0 + r) * ld_inp + k;
+          if (vec_in) v = ldcg4(src);               // layers > 0: row padded to Hq >= k + 4 with zeros
+          else {
+            v.x = __ldcg(src);
+            if (k + 1 < Din) v.y = __ldcg(src + 1);
+            if (k + 2 < Din) v.z = __ldcg(src + 2);
+            if (k + 3 < Din) v.w = __ldcg(src + 3);
+          }
+        }
+        tc::store_split(A_hi, A_lo, r, c4, v);
+      }
+    } else {
+      const int k0 = (c - nci) * tc::KC;
+      for (int it = tid; it < 128 * 8; it += kThreads) {
+        const int r = it >> 3, c4 = it & 7, k = k0 + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nvalid && k < Hq) {
+          const int e1 = rp[r + 1];
+          for (int e = rp[r]; e < e1; ++e) {
+            const float a = __ldcg(Lp.alpha + e);
+            if (a != 0.f) {
+              const float4 h = ldcg4(Hcur + (size_t)D.col[e] * ldh + k);
+              v.x = fmaf(a, h.x, v.x); v.y = fmaf(a, h.y, v.y); v.z = fmaf(a, h.z, v.z); v.w = fmaf(a, h.w, v.w);
+            }
+          }
+        }
+        tc::store_split(A_hi, A_lo, r, c4, v);
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(smem_u32(&T.full_b[s]), (ccur >> 1) & 1u);
+      tc::fence_after_sync();
+      const uint32_t sa = smem_u32(A_hi);
+      const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + 128 * tc::ROW_BYTES);
+      const uint64_t bh = tc::smem_desc(sa + 2 * 128 * tc::ROW_BYTES), bl = tc::smem_desc(sa + 2 * 128 * tc::ROW_BYTES + 192 * tc::ROW_BYTES);
+      if (c < nci) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc::mma3(T.tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc192, c == 0 && ks == 0);
+      } else {
+        const uint64_t nrow = (128 * tc::ROW_BYTES) >> 4;    // B rows 128..191 = n gate
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tc::mma3(T.tmem + 64, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc128, false);
+          tc::mma3(T.tmem + 192, ah + 2 * ks, al + 2 * ks, bh + nrow + 2 * ks, bl + nrow + 2 * ks, idesc64, c == nci && ks == 0);
+        }
+      }
+      tc::commit(&T.mma_done[s]);
+      if (c + 1 < nchunks) {                         // weight chunk c+1 -> other stage once chunk c-1's MMAs are done
+        if (ccur >= 1) mbar_wait(smem_u32(&T.mma_done[s ^ 1u]), ((ccur - 1) >> 1) & 1u);
+        issue_B(ccur + 1, c + 1);
+      }
+    }
+  }
+  T.cc += (uint32_t)nchunks;
+
+  // ---------------- epilogue ----------------
+  {
+    const uint32_t last = T.cc - 1;
+    mbar_wait(smem_u32(&T.mma_done[last & 1u]), (last >> 1) & 1u);
+    tc::fence_after_sync();
+    const int q = warp & 3, hh = warp >> 2;
+    const int r = 32 * q + lane;
+    const bool rok = r < nvalid;
+    const uint32_t tbase = T.tmem + ((uint32_t)(32 * q) << 16);
+    const int HP = P.NS * US;
+    const int e0 = rok ? rp[r] : 0, e1 = rok ? rp[r + 1] : 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int cu = hh * 32 + 8 * j;                 // column inside the 64-unit tile
+      const int u0 = ut * 64 + cu;
+      if (u0 >= Hq) break;                            // warp-uniform
+      float an[8], ar[8], az[8], ah_[8];
+      tc::ld8(tbase + (uint32_t)cu, an);
+      tc::ld8(tbase + 64u + (uint32_t)cu, ar);
+      tc::ld8(tbase + 128u + (uint32_t)cu, az);
+      if (!level0) tc::ld8(tbase + 192u + (uint32_t)cu, ah_);
+      tc::wait_ld();
+      float hp[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) hp[t] = 0.f;
+      if (!level0) {
+        for (int e = e0; e < e1; ++e) {
+          const float a = __ldcg(Lp.alpha + e);
+          if (a != 0.f) {
+            const float* hr = Hcur + (size_t)D.col[e] * ldh + u0;
+            const float4 h0 = ldcg4(hr);
+            float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u0 + 4 < Hq) h1 = ldcg4(hr + 4);
+            hp[0] = fmaf(a, h0.x, hp[0]); hp[1] = fmaf(a, h0.y, hp[1]); hp[2] = fmaf(a, h0.z, hp[2]); hp[3] = fmaf(a, h0.w, hp[3]);
+            hp[4] = fmaf(a, h1.x, hp[4]); hp[5] = fmaf(a, h1.y, hp[5]); hp[6] = fmaf(a, h1.z, hp[6]); hp[7] = fmaf(a, h1.w, hp[7]);
+          }
+        }
+      }
+      float o[8], pk = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int u = u0 + t;
+        const float rg = sigmoidf_(ar[t] + __ldg(Lp.bias + u));
+        const float zg = sigmoidf_(az[t] + __ldg(Lp.bias + HP + u));
+        const float ng = tanhf(an[t] + __ldg(Lp.bias + 2 * HP + u) + rg * ((level0 ? 0.f : ah_[t]) + __ldg(Lp.bias + 3 * HP + u)));
+        o[t] = ng + zg * (hp[t] - ng);
+        pk = fmaf(o[t], __ldg(Lp.wk + u), pk);
+      }
+      if (rok) {
+        float* dst = Lp.Hs + (size_t)(p0 + r) * ldh + u0;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        if (u0 + 4 < Hq) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        Lp.skp[(size_t)(p0 + r) * P.nsk + (u0 >> 3)] = pk;
+      }
+    }
+    tc::fence_before_sync();
   }
 }
 

@@ -3,6 +3,7 @@
 // zero-padded, unit-sliced stream the level kernel bulk-copies, and folds the attention linear layer into
 // a key vector + two edge-type coefficients.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace dagnn {
 
@@ -33,6 +34,43 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
       }
     }
     w[idx] = v;
+  }
+}
+
+// tensor-core image of the GRU weights: per 64-unit tile `ut`, per 32-wide k chunk c (input chunks, then hidden chunks),
+// a hi tile then a lo tile, each [192 gate-unit rows][128 B] in the K-major SWIZZLE_128B layout of tc.cuh — exactly the
+// bytes the level kernel bulk-copies into shared memory and hands to tcgen05.mma as the B operand.
+// Row order: input chunks [n | r | z] (D columns 0..191), hidden chunks [r | z | n] (D columns 64..255).
+__global__ void __launch_bounds__(256) k_pack_tc(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                                 DagnnPackLayout L, float* __restrict__ packed) {
+  const int nci = L.Kin32 / 32, nch = L.Kh32 / 32, nc = nci + nch;
+  const int64_t total = (int64_t)L.UT * nc * 192 * 32;          // one thread-iteration per (ut, c, row j, kk)
+  float* img = packed + L.tc_off;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % 32);
+    const int j = (int)((idx / 32) % 192);
+    const int c = (int)((idx / (32 * 192)) % nc);
+    const int ut = (int)(idx / ((int64_t)32 * 192 * nc));
+    const int unit = ut * 64 + (j & 63);
+    const int jb = j >> 6;
+    float w = 0.f;
+    if (unit < L.H) {
+      if (c < nci) {
+        const int g = jb == 0 ? 2 : jb - 1;
+        const int k = c * 32 + kk;
+        if (k < L.Din) w = w_ih[((size_t)g * L.H + unit) * L.Din + k];
+      } else {
+        const int g = jb;
+        const int k = (c - nci) * 32 + kk;
+        if (k < L.H) w = w_hh[((size_t)g * L.H + unit) * L.H + k];
+      }
+    }
+    const float hi = tc::tf32_rn(w);
+    const float lo = w - hi;
+    const size_t tile = ((size_t)ut * nc + c) * 2 * (192 * 32);
+    const uint32_t off = ((uint32_t)(j >> 3) * 1024u + (uint32_t)(j & 7) * 128u + ((uint32_t)((kk >> 2) ^ (j & 7)) << 4) + (uint32_t)(kk & 3) * 4u) >> 2;
+    img[tile + off] = hi;
+    img[tile + 192 * 32 + off] = lo;
   }
 }
 
@@ -91,6 +129,11 @@ extern "C" int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPack
   L.wk_off = off;    off += HP;
   L.attnc_off = off; off += 4;
   L.vidk_off = off;  off += round_up64(nvid, 4);
+  L.Kin32 = round_up(Din, 32);
+  L.Kh32 = round_up(H, 32);
+  L.UT = ceil_div(H, 64);
+  off = round_up64(off, 256);                                  // 1024-byte aligned images (bulk copies need 16)
+  L.tc_off = off;    off += (int64_t)L.UT * ((L.Kin32 + L.Kh32) / 32) * 2 * (192 * 32);
   L.total_floats = off;
   *out = L;
   return DAGNN_OK;
@@ -107,6 +150,9 @@ extern "C" int dagnn_pack_params_f32(const float* weight_ih, const float* weight
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   k_pack_weights<<<blocks, 256, 0, st>>>(weight_ih, weight_hh, *layout, packed);
   if (int rc = check_launch("k_pack_weights")) return rc;
+  const int64_t ttc = (int64_t)layout->UT * ((layout->Kin32 + layout->Kh32) / 32) * 192 * 32;
+  k_pack_tc<<<(int)((ttc + 255) / 256 < 148 * 8 ? (ttc + 255) / 256 : 148 * 8), 256, 0, st>>>(weight_ih, weight_hh, *layout, packed);
+  if (int rc = check_launch("k_pack_tc")) return rc;
   k_pack_small<<<1, 256, 0, st>>>(bias_ih, bias_hh, attn_w, Dq, edge_w, *layout, packed);
   return check_launch("k_pack_small");
 }

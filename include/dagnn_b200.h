@@ -106,10 +106,14 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
  *   wk    [NS*32]               key weights on the hidden state
  *   attnc [4]                   {wk·W_e[:,0], wk·W_e[:,1], 0, 0}
  *   vidk  [nvid]                key weights on the one-hot vertex id (D-VAE NA), nvid may be 0
+ *   tc    [UT][(Kin32+Kh32)/32][hi,lo][192 rows][32 k]  tf32 hi / lo split of the same weights as K-major
+ *                               SWIZZLE_128B shared-memory images for tcgen05.mma (UT = ceil(H/64) unit tiles;
+ *                               rows = [n|r|z] x 64 units for input chunks, [r|z|n] for hidden chunks)
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnPackLayout {
   int32_t Din, H, Kin, Kh, NS, nvid;
-  int64_t w_off, bias_off, wk_off, attnc_off, vidk_off, total_floats;
+  int32_t Kin32, Kh32, UT, reserved;   /* tensor-core image: K padded to 32, UT = ceil(H/64) unit tiles */
+  int64_t w_off, bias_off, wk_off, attnc_off, vidk_off, tc_off, total_floats;
 } DagnnPackLayout;
 
 int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out);
