@@ -30,7 +30,7 @@ constexpr int kThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kWSliceFloats = BK * 3 * US;      // 1536 floats = one k-block of one 32-unit slice
 constexpr int kWSliceBytes = kWSliceFloats * 4; // 6144
-constexpr int kWStageFloats = kWSliceFloats;     // one ring stage = one k-block of one slice
+constexpr int kWStageFloats = 2 * kWSliceFloats; // a ring stage holds up to two slices (64-unit tiles)
 constexpr int kBarBytes = 128;                  // 8 ring barriers + tensor-core path: full_b[2], mma_done[2]
 constexpr int kTcStageBytes = 2 * 128 * tc::ROW_BYTES + 2 * 192 * tc::ROW_BYTES;   // A hi/lo + B hi/lo = 80 KB
 constexpr int kTcBytes = 2 * kTcStageBytes + 1024;                                 // two stages + row-pointer cache
