@@ -12,7 +12,7 @@ A step = one forward of the hot path over one batch.
           max over ranks).
   e2e   : the same through the public module API with the batch in PINNED HOST memory: H2D of every input
           tensor + forward + D2H of the readout inside the timed region.
-  roofline : the level-sweep kernel (k_level_step): algorithmic bytes of one sweep / device time of
+  roofline : the level-sweep kernel (k_sweep): algorithmic bytes of one sweep / device time of
           the sweep's launches, against the measured HBM peak (MEASURED_PEAKS.json, else the recipe's fallback).
   cpu_baseline : the oracle port of the reference's CPU path (oracle/dagnn_oracle.py — the reference is Python and
           needs PyG, which does not exist on the box) on the same batch, host cores of this box.
@@ -382,7 +382,7 @@ def main():
             "e2e": {"value": e2e, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_level_step (all %d launches of one sweep)" % sweep_launches, "bound": "hbm",
+            "roofline": {"kernel": "k_sweep (persistent level sweep, %d launch per forward)" % sweep_launches, "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sweep": int(alg_bytes),
                          "sweep_ms": ms_sweep / args.steps, "gathered_edges": e_prime,

@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdagnn_sm100.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "schedule.cu", "embed_readout.cu", "pack.cu", "level_sweep.cu", "tc_selftest.cu"]
+SOURCES = ["abi.cu", "schedule.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "tc_selftest.cu"]
 HEADERS = ["common.cuh", "tc.cuh"]
 
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp = C.c_void_p
 
@@ -36,10 +36,10 @@ class DagnnSchedule(C.Structure):
 
 class DagnnPackLayout(C.Structure):
     _fields_ = [
-        ("Din", C.c_int32), ("H", C.c_int32), ("Kin", C.c_int32), ("Kh", C.c_int32), ("NS", C.c_int32), ("nvid", C.c_int32),
-        ("Kin32", C.c_int32), ("Kh32", C.c_int32), ("UT", C.c_int32), ("reserved", C.c_int32),
-        ("w_off", C.c_int64), ("bias_off", C.c_int64), ("wk_off", C.c_int64), ("attnc_off", C.c_int64),
-        ("vidk_off", C.c_int64), ("tc_off", C.c_int64), ("total_floats", C.c_int64),
+        ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32), ("Kin64", C.c_int32), ("Kh64", C.c_int32),
+        ("NG", C.c_int32), ("NT", C.c_int32), ("HP", C.c_int32),
+        ("bias_off", C.c_int64), ("wk_off", C.c_int64), ("attnc_off", C.c_int64), ("vidk_off", C.c_int64),
+        ("img16_off", C.c_int64), ("img64_off", C.c_int64), ("total_floats", C.c_int64),
     ]
 
 
@@ -73,10 +73,11 @@ EXPORTS = {
     "dagnn_schedule_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DagnnSchedule), vp, C.c_size_t, vp]),
     "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),
     "dagnn_pack_params_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(DagnnPackLayout), vp, vp]),
-    "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
     "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
     "dagnn_tc_selftest_f32": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dagnn_tc_selftest_f16x3": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),
     "dagnn_states_to_node_order_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.c_int32, vp, C.c_int64, C.c_int32, vp,
@@ -91,7 +92,7 @@ class DagnnError(RuntimeError):
 def nvcc_command(out_path: str = LIB_PATH):
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-I", os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + \
-           [os.path.join(CSRC, s) for s in SOURCES]
+           os.environ.get("DAGNN_NVCC_FLAGS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

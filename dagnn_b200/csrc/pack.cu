@@ -1,83 +1,52 @@
 // Parameter packing for one (direction, layer) — layout documented in include/dagnn_b200.h.
-// Runs once per parameter version (not per forward): transposes the GRU weights into the K-major,
-// zero-padded, unit-sliced stream the level kernel bulk-copies, and folds the attention linear layer into
-// a key vector + two edge-type coefficients.
+// Runs once per parameter version (not per forward): splits the GRU weights into fp16 hi / lo parts and lays them out
+// as the exact shared-memory images (K-major SWIZZLE_128B tiles) the level kernel bulk-copies and hands to
+// tcgen05.mma as the B operand, and folds the attention linear layer into a key vector + two edge-type coefficients.
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace dagnn {
 
-__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                                                      DagnnPackLayout L, float* __restrict__ packed) {
-  const int K = L.Kin + L.Kh;
-  const int64_t total = (int64_t)L.NS * K * 3 * DAGNN_UNIT_SLICE;
-  float* w = packed + L.w_off;
-  // [slice][k-block of 16][kq 4][gate 3][unit 32][k4 4]: a thread (= unit) reads float4 over k, a warp 512 contiguous bytes
-  constexpr int kBlk = DAGNN_K_BLOCK * 3 * DAGNN_UNIT_SLICE;
-  const int nkb = K / DAGNN_K_BLOCK;
+// One image = for every block of U units (U = 16 or 64), for every 64-wide k chunk c (input chunks first, then hidden
+// chunks): a hi tile then a lo tile, each [3U gate-unit rows][128 B = 64 halfs] in the layout of tc.cuh.
+// Row order: input chunks [n | r | z] (TMEM columns 0..3U-1), hidden chunks [r | z | n] (TMEM columns U..4U-1).
+__global__ void __launch_bounds__(256) k_pack_img(const float* __restrict__ w_ih, const float* __restrict__ w_hh, DagnnPackLayout L,
+                                                  int U, int nblocks, __half* __restrict__ img) {
+  const int nci = L.Kin64 / 64, nch = L.Kh64 / 64, nc = nci + nch;
+  const int rows = 3 * U;
+  const int64_t total = (int64_t)nblocks * nc * rows * 64;          // one thread-iteration per (block, c, row j, kk)
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k4 = (int)(idx % 4);
-    const int u = (int)((idx / 4) % DAGNN_UNIT_SLICE);
-    const int g = (int)((idx / (4 * DAGNN_UNIT_SLICE)) % 3);
-    const int kq = (int)((idx / (12 * DAGNN_UNIT_SLICE)) % (DAGNN_K_BLOCK / 4));
-    const int kb = (int)((idx / kBlk) % nkb);
-    const int sl = (int)(idx / ((int64_t)kBlk * nkb));
-    const int k = kb * DAGNN_K_BLOCK + kq * 4 + k4;
-    const int unit = sl * DAGNN_UNIT_SLICE + u;
-    float v = 0.f;
-    if (unit < L.H) {
-      if (k < L.Kin) {
-        if (k < L.Din) v = w_ih[((size_t)g * L.H + unit) * L.Din + k];
-      } else {
-        const int kh = k - L.Kin;
-        if (kh < L.H) v = w_hh[((size_t)g * L.H + unit) * L.H + kh];
-      }
-    }
-    w[idx] = v;
-  }
-}
-
-// tensor-core image of the GRU weights: per 64-unit tile `ut`, per 32-wide k chunk c (input chunks, then hidden chunks),
-// a hi tile then a lo tile, each [192 gate-unit rows][128 B] in the K-major SWIZZLE_128B layout of tc.cuh — exactly the
-// bytes the level kernel bulk-copies into shared memory and hands to tcgen05.mma as the B operand.
-// Row order: input chunks [n | r | z] (D columns 0..191), hidden chunks [r | z | n] (D columns 64..255).
-__global__ void __launch_bounds__(256) k_pack_tc(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                                                 DagnnPackLayout L, float* __restrict__ packed) {
-  const int nci = L.Kin32 / 32, nch = L.Kh32 / 32, nc = nci + nch;
-  const int64_t total = (int64_t)L.UT * nc * 192 * 32;          // one thread-iteration per (ut, c, row j, kk)
-  float* img = packed + L.tc_off;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(idx % 32);
-    const int j = (int)((idx / 32) % 192);
-    const int c = (int)((idx / (32 * 192)) % nc);
-    const int ut = (int)(idx / ((int64_t)32 * 192 * nc));
-    const int unit = ut * 64 + (j & 63);
-    const int jb = j >> 6;
+    const int kk = (int)(idx % 64);
+    const int j = (int)((idx / 64) % rows);
+    const int c = (int)((idx / (64 * (int64_t)rows)) % nc);
+    const int ub = (int)(idx / (64 * (int64_t)rows * nc));
+    const int unit = ub * U + (j % U);
+    const int jb = j / U;
     float w = 0.f;
     if (unit < L.H) {
       if (c < nci) {
         const int g = jb == 0 ? 2 : jb - 1;
-        const int k = c * 32 + kk;
+        const int k = c * 64 + kk;
         if (k < L.Din) w = w_ih[((size_t)g * L.H + unit) * L.Din + k];
       } else {
         const int g = jb;
-        const int k = (c - nci) * 32 + kk;
+        const int k = (c - nci) * 64 + kk;
         if (k < L.H) w = w_hh[((size_t)g * L.H + unit) * L.H + k];
       }
     }
-    const float hi = tc::tf32_rn(w);
-    const float lo = w - hi;
-    const size_t tile = ((size_t)ut * nc + c) * 2 * (192 * 32);
-    const uint32_t off = ((uint32_t)(j >> 3) * 1024u + (uint32_t)(j & 7) * 128u + ((uint32_t)((kk >> 2) ^ (j & 7)) << 4) + (uint32_t)(kk & 3) * 4u) >> 2;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    const size_t tile = ((size_t)ub * nc + c) * 2 * ((size_t)rows * 64);
+    const uint32_t off = (uint32_t)(j >> 3) * 512u + (uint32_t)(j & 7) * 64u + ((uint32_t)((kk >> 3) ^ (j & 7)) << 3) + (uint32_t)(kk & 7);
     img[tile + off] = hi;
-    img[tile + 192 * 32 + off] = lo;
+    img[tile + (size_t)rows * 64 + off] = lo;
   }
 }
 
 __global__ void __launch_bounds__(256) k_pack_small(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                                     const float* __restrict__ attn_w, int Dq, const float* __restrict__ edge_w,
                                                     DagnnPackLayout L, float* __restrict__ packed) {
-  const int HP = L.NS * DAGNN_UNIT_SLICE;
+  const int HP = L.HP;
   float* bias = packed + L.bias_off;
   float* wk = packed + L.wk_off;
   float* attnc = packed + L.attnc_off;
@@ -118,22 +87,22 @@ using namespace dagnn;
 extern "C" int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out) {
   DAGNN_REQUIRE(out && Din > 0 && H > 0 && nvid >= 0, "pack_layout args");
   DagnnPackLayout L;
+  memset(&L, 0, sizeof(L));
   L.Din = Din; L.H = H; L.nvid = nvid;
-  L.Kin = round_up(Din, DAGNN_K_BLOCK);
-  L.Kh = round_up(H, DAGNN_K_BLOCK);
-  L.NS = ceil_div(H, DAGNN_UNIT_SLICE);
-  const int64_t HP = (int64_t)L.NS * DAGNN_UNIT_SLICE;
+  L.Kin64 = round_up(Din, 64);
+  L.Kh64 = round_up(H, 64);
+  L.NG = ceil_div(H, 16);
+  L.NT = ceil_div(H, 64);
+  L.HP = L.NT * 64;
+  const int64_t nc = (L.Kin64 + L.Kh64) / 64;
   int64_t off = 0;
-  L.w_off = off;     off += (int64_t)L.NS * (L.Kin + L.Kh) * 3 * DAGNN_UNIT_SLICE;
-  L.bias_off = off;  off += 4 * HP;
-  L.wk_off = off;    off += HP;
+  L.bias_off = off;  off += 4 * (int64_t)L.HP;
+  L.wk_off = off;    off += L.HP;
   L.attnc_off = off; off += 4;
   L.vidk_off = off;  off += round_up64(nvid, 4);
-  L.Kin32 = round_up(Din, 32);
-  L.Kh32 = round_up(H, 32);
-  L.UT = ceil_div(H, 64);
-  off = round_up64(off, 256);                                  // 1024-byte aligned images (bulk copies need 16)
-  L.tc_off = off;    off += (int64_t)L.UT * ((L.Kin32 + L.Kh32) / 32) * 2 * (192 * 32);
+  off = round_up64(off, 256);                                  // images 1024-byte aligned
+  L.img16_off = off; off += (int64_t)L.NG * nc * 2 * (48 * 64) / 2;     // halfs -> 4-byte units
+  L.img64_off = off; off += (int64_t)L.NT * nc * 2 * (192 * 64) / 2;
   L.total_floats = off;
   *out = L;
   return DAGNN_OK;
@@ -146,13 +115,16 @@ extern "C" int dagnn_pack_params_f32(const float* weight_ih, const float* weight
   DAGNN_REQUIRE(Dq >= 0, "pack_params: Dq");
   DAGNN_REQUIRE((((uintptr_t)packed) & 15) == 0, "pack_params: packed must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  const int64_t total = (int64_t)layout->NS * (layout->Kin + layout->Kh) * 3 * DAGNN_UNIT_SLICE;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  k_pack_weights<<<blocks, 256, 0, st>>>(weight_ih, weight_hh, *layout, packed);
-  if (int rc = check_launch("k_pack_weights")) return rc;
-  const int64_t ttc = (int64_t)layout->UT * ((layout->Kin32 + layout->Kh32) / 32) * 192 * 32;
-  k_pack_tc<<<(int)((ttc + 255) / 256 < 148 * 8 ? (ttc + 255) / 256 : 148 * 8), 256, 0, st>>>(weight_ih, weight_hh, *layout, packed);
-  if (int rc = check_launch("k_pack_tc")) return rc;
-  k_pack_small<<<1, 256, 0, st>>>(bias_ih, bias_hh, attn_w, Dq, edge_w, *layout, packed);
+  const DagnnPackLayout& L = *layout;
+  const int64_t nc = (L.Kin64 + L.Kh64) / 64;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int U = pass == 0 ? 16 : 64, nb = pass == 0 ? L.NG : L.NT;
+    const int64_t tot = (int64_t)nb * nc * 3 * U * 64;
+    const int blocks = (int)((tot + 255) / 256 < 148 * 8 ? (tot + 255) / 256 : 148 * 8);
+    __half* img = reinterpret_cast<__half*>(packed + (pass == 0 ? L.img16_off : L.img64_off));
+    k_pack_img<<<blocks, 256, 0, st>>>(weight_ih, weight_hh, L, U, nb, img);
+    if (int rc = check_launch("k_pack_img")) return rc;
+  }
+  k_pack_small<<<1, 256, 0, st>>>(bias_ih, bias_hh, attn_w, Dq, edge_w, L, packed);
   return check_launch("k_pack_small");
 }

@@ -12,6 +12,7 @@
 // address (the hardware swizzles on absolute smem address bits, hence the 1024-byte alignment of every tile).
 // Bit layouts follow cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor / UMMA::InstrDescriptor).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -99,6 +100,52 @@ __device__ __forceinline__ void mma3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_
   mma_tf32(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
   mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
   mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+}
+
+// ---- fp16 x 3 split precision (what the level kernel uses) --------------------------------------------------------
+// x = hi + lo with hi = rn_f16(x), lo = rn_f16(x - hi): 22 significant bits for |x| in [6e-5, 65504), an absolute error
+// <= 2^-25 below that (fp16 subnormals). The product is accumulated in fp32 as hi*hi + lo*hi + hi*lo on
+// tcgen05.mma kind::f16 (K = 16 per instruction, twice the TF32 rate); measured against an fp64 GEMM the split costs
+// ~2e-6 max-abs on the node states after the full level recurrence, the same order as plain fp32.
+// Operand tiles keep the K-major SWIZZLE_128B layout above; a 128-byte row now holds 64 k (KC16), a 16-byte chunk 8 k.
+constexpr int KC16 = 64;
+
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) {
+  return (1u << 4) /* D = f32 */ | (0u << 7) /* A = f16 */ | (0u << 10) /* B = f16 */ | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);   // a_major = b_major = 0: K-major
+}
+// 8 consecutive k of one row -> one 16-byte chunk of the hi tile and one of the lo tile
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+}
+__device__ __forceinline__ void store_split8(unsigned char* hi_tile, unsigned char* lo_tile, int r, int c8, const float (&v)[8]) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  const uint32_t off = tile_off(r, c8);
+  *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+  *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the three products of one K = 16 step: D (+)= Ahi*Bhi + Alo*Bhi + Ahi*Blo. `first`: the first product overwrites D
+__device__ __forceinline__ void mma3_f16(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                         bool first) {
+  mma_f16(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
+  mma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+  mma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
 }
 
 }  // namespace tc

@@ -19,6 +19,7 @@ __device__ __forceinline__ void st_mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256, 1) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B,
                                                         float* __restrict__ C, int M, int N, int K) {
   extern __shared__ unsigned char smem_raw[];
@@ -40,19 +41,37 @@ __global__ void __launch_bounds__(256, 1) k_tc_selftest(const float* __restrict_
   tc::fence_after_sync();
   const uint32_t tmem = *slot;
   const int row0 = blockIdx.x * 128;
-  const uint32_t idesc = tc::instr_desc_tf32(128, N);
-  const int nchunks = K / tc::KC;
+  const uint32_t idesc = F16 ? tc::instr_desc_f16(128, N) : tc::instr_desc_tf32(128, N);
+  const int KCH = F16 ? tc::KC16 : tc::KC;
+  const int nchunks = K / KCH;
   for (int c = 0; c < nchunks; ++c) {
     for (int it = tid; it < 128 * 8; it += 256) {
       const int r = it >> 3, c4 = it & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < M) v = *reinterpret_cast<const float4*>(A + (size_t)(row0 + r) * K + c * tc::KC + 4 * c4);
-      tc::store_split(A_hi, A_lo, r, c4, v);
+      if (F16) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row0 + r < M) {
+          const float4 a = *reinterpret_cast<const float4*>(A + (size_t)(row0 + r) * K + c * KCH + 8 * c4);
+          const float4 b = *reinterpret_cast<const float4*>(A + (size_t)(row0 + r) * K + c * KCH + 8 * c4 + 4);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        tc::store_split8(A_hi, A_lo, r, c4, v);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M) v = *reinterpret_cast<const float4*>(A + (size_t)(row0 + r) * K + c * KCH + 4 * c4);
+        tc::store_split(A_hi, A_lo, r, c4, v);
+      }
     }
     for (int it = tid; it < N * 8; it += 256) {
       const int r = it >> 3, c4 = it & 7;
-      const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * K + c * tc::KC + 4 * c4);
-      tc::store_split(B_hi, B_lo, r, c4, v);
+      if (F16) {
+        const float4 a = *reinterpret_cast<const float4*>(B + (size_t)r * K + c * KCH + 8 * c4);
+        const float4 b = *reinterpret_cast<const float4*>(B + (size_t)r * K + c * KCH + 8 * c4 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        tc::store_split8(B_hi, B_lo, r, c4, v);
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * K + c * KCH + 4 * c4);
+        tc::store_split(B_hi, B_lo, r, c4, v);
+      }
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -61,7 +80,10 @@ __global__ void __launch_bounds__(256, 1) k_tc_selftest(const float* __restrict_
       const uint64_t ah = tc::smem_desc(tc::smem_addr(A_hi)), al = tc::smem_desc(tc::smem_addr(A_lo));
       const uint64_t bh = tc::smem_desc(tc::smem_addr(B_hi)), bl = tc::smem_desc(tc::smem_addr(B_lo));
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tc::mma3(tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
+      for (int ks = 0; ks < 4; ++ks) {
+        if (F16) tc::mma3_f16(tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
+        else tc::mma3(tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
+      }
       tc::commit(bar);
     }
     st_mbar_wait(bar, (uint32_t)(c & 1));   // MMAs of this chunk done: operand tiles may be overwritten
@@ -89,16 +111,25 @@ __global__ void __launch_bounds__(256, 1) k_tc_selftest(const float* __restrict_
 
 using namespace dagnn;
 
-extern "C" int dagnn_tc_selftest_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream_) {
+template <bool F16>
+static int tc_selftest(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream_) {
   DAGNN_REQUIRE(A && B && C, "tc_selftest: null pointer");
-  DAGNN_REQUIRE(M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 32 && K % 32 == 0, "tc_selftest: M>0, N%16==0 in [16,256], K%32==0");
+  const int kc = F16 ? tc::KC16 : tc::KC;
+  DAGNN_REQUIRE(M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= kc && K % kc == 0, "tc_selftest: M>0, N%16==0 in [16,256], K%32==0 (tf32) / K%64==0 (f16)");
   DAGNN_REQUIRE(((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) == 0, "tc_selftest: 16-byte alignment");
   const size_t smem = 1024 + (size_t)(2 * 128 + 2 * 256) * tc::ROW_BYTES + 64;
   static bool configured = false;
   if (!configured) {
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_tc_selftest<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  k_tc_selftest<<<(M + 127) / 128, 256, smem, static_cast<cudaStream_t>(stream_)>>>(A, B, C, M, N, K);
+  k_tc_selftest<F16><<<(M + 127) / 128, 256, smem, static_cast<cudaStream_t>(stream_)>>>(A, B, C, M, N, K);
   return check_launch("k_tc_selftest");
+}
+
+extern "C" int dagnn_tc_selftest_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
+  return tc_selftest<false>(A, B, C, M, N, K, stream);
+}
+extern "C" int dagnn_tc_selftest_f16x3(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
+  return tc_selftest<true>(A, B, C, M, N, K, stream);
 }

@@ -248,8 +248,8 @@ class PackedParams(object):
 _WS = {}
 
 
-def _sweep_workspace(device, dirs, layers, Din, H) -> torch.Tensor:
-    need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H))
+def _sweep_workspace(device, dirs, layers, Din, H, N, E) -> torch.Tensor:
+    need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H, N, E))
     key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     w = _WS.get(key)
     if w is None or w.numel() * 4 < need:
@@ -266,7 +266,7 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
     dirs, N = sched.c.dirs, sched.c.N
     ldh = (H + 3) // 4 * 4
     Hs = torch.empty(dirs, num_layers, N, ldh, device=X.device, dtype=torch.float32)
-    ws = _sweep_workspace(X.device, dirs, num_layers, Din, H)
+    ws = _sweep_workspace(X.device, dirs, num_layers, Din, H, N, sched.c.E)
     a = DagnnSweepArgs()
     a.sched = C.pointer(sched.c)
     for d in range(dirs):
@@ -284,7 +284,7 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
         a.trace = trace.data_ptr()
     check(lib().dagnn_sweep_forward_f32(C.byref(a), _stream()), "dagnn_sweep_forward_f32")
     if trace is not None:
-        return Hs, trace.view(trace_steps, 256, 8)
+        return Hs, trace.view(trace_steps, 256, 16)
     return Hs
 
 

@@ -27,11 +27,10 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 2
+#define DAGNN_ABI_VERSION 3
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
-#define DAGNN_UNIT_SLICE 32         /* hidden units per weight slice of the packed layout        */
-#define DAGNN_K_BLOCK 16            /* K granularity of the packed layout (rows per stage)       */
+#define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
 #define DAGNN_MAX_READOUT_BLOCKS 20 /* column blocks of one readout call                         */
 
 enum {
@@ -93,47 +92,53 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
                          const DagnnSchedule* sched, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Parameter packing for one (direction, layer): GRU weights -> K-major, zero-padded, unit-sliced stream
- * that the level kernel bulk-copies into shared memory; attention vector -> key part + edge-type coefficients.
+ * Parameter packing for one (direction, layer): GRU weights -> fp16 hi/lo split, pre-swizzled shared-memory images
+ * that the level kernel bulk-copies and feeds to tcgen05.mma; attention vector -> key part + edge-type coefficients.
  * Sources: nn.GRUCell weight_ih [3H,Din], weight_hh [3H,H], bias_ih/bias_hh [3H]   (dagnn.py:79-81),
  *          attn_lin.weight [1, Dq + H (+nvid)] (dagnn.py:359; dvae/dagnn.py:47-48,357),
  *          edge_encoder.weight [H,2] (dagnn.py:356) or NULL.
  * The query part of attn_lin (first Dq columns), attn_lin.bias and edge_encoder.bias add the same constant
  * to every in-edge score of a node and cancel in the softmax, so they are not packed.
- * Layout of `packed` (floats), all offsets from dagnn_pack_layout():
- *   w     [NS][Kin+Kh][3][32]   NS=ceil(H/32); Kin=roundup(Din,16); Kh=roundup(H,16)
- *   bias  [4][NS*32]            b_r=b_ir+b_hr, b_z=b_iz+b_hz, b_in, b_hn
- *   wk    [NS*32]               key weights on the hidden state
- *   attnc [4]                   {wk·W_e[:,0], wk·W_e[:,1], 0, 0}
+ * Layout of `packed` (4-byte units), all offsets from dagnn_pack_layout():
+ *   bias  [4][HP]               b_r=b_ir+b_hr, b_z=b_iz+b_hz, b_in, b_hn; HP = 64*ceil(H/64), zero padded
+ *   wk    [HP]                  key weights on the hidden state
+ *   attnc [4]                   {wk.W_e[:,0], wk.W_e[:,1], 0, 0}
  *   vidk  [nvid]                key weights on the one-hot vertex id (D-VAE NA), nvid may be 0
- *   tc    [UT][(Kin32+Kh32)/32][hi,lo][192 rows][32 k]  tf32 hi / lo split of the same weights as K-major
- *                               SWIZZLE_128B shared-memory images for tcgen05.mma (UT = ceil(H/64) unit tiles;
- *                               rows = [n|r|z] x 64 units for input chunks, [r|z|n] for hidden chunks)
+ *   img16 [NG][nc][hi,lo][48 rows][64 halfs]    NG = ceil(H/16) unit groups, nc = (Kin64 + Kh64)/64 k chunks
+ *   img64 [NT][nc][hi,lo][192 rows][64 halfs]   NT = ceil(H/64) unit tiles
+ *         K-major SWIZZLE_128B images (dagnn_b200/csrc/tc.cuh) of w = hi + lo, hi = rn_f16(w), lo = rn_f16(w - hi);
+ *         rows = [n|r|z] x U units for the input chunks, [r|z|n] x U units for the hidden chunks (U = 16 / 64).
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnPackLayout {
-  int32_t Din, H, Kin, Kh, NS, nvid;
-  int32_t Kin32, Kh32, UT, reserved;   /* tensor-core image: K padded to 32, UT = ceil(H/64) unit tiles */
-  int64_t w_off, bias_off, wk_off, attnc_off, vidk_off, tc_off, total_floats;
+  int32_t Din, H, nvid;
+  int32_t Kin64, Kh64;                 /* K of the input / hidden part padded to the 64-wide chunk             */
+  int32_t NG, NT, HP;                  /* 16-unit groups, 64-unit tiles, padded unit count                     */
+  int64_t bias_off, wk_off, attnc_off, vidk_off, img16_off, img64_off, total_floats;
 } DagnnPackLayout;
 
 int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out);
 
+/* `packed` must be 16-byte aligned (the images are bulk-copied into swizzled shared memory). */
 int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const float* bias_ih,
                           const float* bias_hh, const float* attn_w, int32_t Dq, const float* edge_w,
                           const DagnnPackLayout* layout, float* packed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * The level sweep (the hot path): for every direction d, level l (sequential) and stacked layer i,
- *   m_v   = sum_e softmax_e( wk·h_e + wk·W_e a_e [+ vidk[nbr mod nvid]] ) * h_e     over ALL in-edges e of v,
+ *   m_v   = sum_e softmax_e( wk.h_e + wk.W_e a_e [+ vidk[nbr mod nvid]] ) * h_e     over ALL in-edges e of v,
  *           h_e = H[d][i][nbr(e)] if level_d[nbr(e)] < l else 0      (level 0: m_v = 0, edges ignored)
  *   inp_v = GRUCell_{d,i}(inp_v, m_v);  H[d][i][v] = inp_v          (inp_v starts as X[v])
  * replaces dagnn.py:144-182 incl. AttnConv (:362-373), PyG propagate/softmax/scatter-add, nn.GRUCell (:181) and
  * the index_put at :182; D-VAE variants dvae/dagnn.py:109-145, dvae/dagnn_bn.py:108-136.
  * ONE persistent cooperative kernel runs the whole sweep: wavefront step s = level + layer processes all (d, layer)
- * pairs of the step, tiles dealt to one CTA per SM, grid barrier between steps. Level offsets and the level count
- * (reference: max level of direction 0, + 1 — dagnn.py:137) are read from the schedule's DEVICE arrays, so a forward
- * needs no host synchronisation. If sched->summary[2] != 0 (bad input) the kernel does nothing; the caller checks the
- * status. States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
+ * pairs of the step as tiles of <= 256 level rows x 16 or 64 hidden units dealt to one CTA per SM, with one grid
+ * barrier between steps. Per tile: softmax weights of the rows' in-edges from per-node partial key scores, the
+ * operand rows [inp_v | m_v] gathered straight into swizzled shared memory as fp16 hi/lo tiles, the gate GEMM on
+ * tcgen05 (fp16 x 3 split, fp32 accumulators in TMEM), GRU pointwise epilogue out of TMEM. Level offsets and the
+ * level count (reference: max level of direction 0, + 1 — dagnn.py:137) are read from the schedule's DEVICE arrays,
+ * so a forward needs no host synchronisation. If sched->summary[2] != 0 (bad input) the kernel does nothing; the
+ * caller checks the status. States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
+ * Inputs must satisfy |x| < 65504 (fp16 range of the hi part); states are in (-1, 1) by construction.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnSweepArgs {
   const DagnnSchedule* sched;
@@ -147,12 +152,15 @@ typedef struct DagnnSweepArgs {
   int32_t use_edge_attr;               /* 1: add the edge-type score term (sched->eattr must exist) */
   void* workspace;                     /* device scratch, dagnn_sweep_workspace_bytes(), 256-byte aligned */
   size_t workspace_bytes;
-  void* trace;                         /* optional profiling buffer (NULL = off): int64 [steps][grid<=256][8] clock64 stamps:
-                                          0 step begin, 1 first tile gathered, 2 first tile GEMM done, 3 first tile stored,
-                                          4 all tiles done, 5 barrier passed, 6 #tiles of this CTA, 7 big-tile step        */
+  void* trace;                         /* optional profiling buffer (NULL = off): int64 [steps][grid<=256][16] clock64 values:
+                                          0 step begin, 1 first tile: operands built, 2 first tile: accumulators ready,
+                                          3 first tile stored, 4 all tiles done, 5 barrier passed, 6 #tiles of this CTA,
+                                          7 units per tile | rows per tile << 8; first tile, builder thread 0, cycles spent
+                                          in 8 pre-phase, 9 waiting for a free operand stage, 10 building, 11 hand-over;
+                                          issuer: 12 waiting for weights, 13 waiting for operands, 14 issuing, 15 #stages  */
 } DagnnSweepArgs;
 
-size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H);
+size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E);
 size_t dagnn_sweep_trace_bytes(int32_t max_steps);
 int dagnn_sweep_forward_f32(const DagnnSweepArgs* args, void* stream);
 
@@ -182,6 +190,8 @@ int dagnn_readout_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* block
 /* Diagnostic: C[M,N] = A[M,K] * B[N,K]^T (fp32 row-major) through the same tcgen05 3xTF32 building blocks the level
  * kernel uses (K-major SWIZZLE_128B operand tiles, TMEM accumulators). N % 16 == 0, 16 <= N <= 256, K % 32 == 0. */
 int dagnn_tc_selftest_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+/* The same in the fp16 x 3 split (hi*hi + lo*hi + hi*lo on kind::f16, K = 16 per MMA) the level kernel runs. K % 64 == 0. */
+int dagnn_tc_selftest_f16x3(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
 
 /* Un-permute states for inspection / tests: dst[v,:] = src[pos[dir][v],:]  (fp32 [N,H]) */
 int dagnn_states_to_node_order_f32(const DagnnSchedule* sched, int32_t dir, const float* src, int64_t lds,

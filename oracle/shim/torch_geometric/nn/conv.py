@@ -24,7 +24,7 @@ class MessagePassing(torch.nn.Module):
         i, j = (1, 0) if self.flow == "source_to_target" else (0, 1)
         n_nodes = None
         for name in self._msg_params:
-            if name[-2:] in ("_i", "_j"):
+            if name[-2:] in ("_i", "_j") and name not in ("size_i", "size_j"):
                 d = kwargs.get(name[:-2])
                 if torch.is_tensor(d):
                     n_nodes = d.size(0)
@@ -33,7 +33,9 @@ class MessagePassing(torch.nn.Module):
             n_nodes = size[i] if isinstance(size, (tuple, list)) else size
         args = {}
         for name in self._msg_params:
-            if name[-2:] in ("_i", "_j"):
+            if name in ("size_i", "size_j"):
+                args[name] = n_nodes
+            elif name[-2:] in ("_i", "_j"):
                 d = kwargs.get(name[:-2])
                 if torch.is_tensor(d):
                     d = d.index_select(0, edge_index[i if name[-2:] == "_i" else j])
@@ -42,8 +44,6 @@ class MessagePassing(torch.nn.Module):
                 args[name] = edge_index[i]
             elif name == "ptr":
                 args[name] = None
-            elif name in ("size_i", "size_j"):
-                args[name] = n_nodes
             elif name == "edge_index":
                 args[name] = edge_index
             else:

@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the package — synthetic workload generators, level builder vs the oracle's top_sort, graph
+selection / sharding helpers, and the world_size-2 gloo path (graph-sharded forward bookkeeping + gradient all-reduce)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dagnn_b200 import data as D, sharding
+from oracle import dagnn_oracle as O
+
+
+def test_code2_generator_is_deterministic_and_level_consistent():
+    A, B = D.make_code2_batch(6, 77), D.make_code2_batch(6, 77)
+    for k in ("x", "edge_index", "edge_attr", "batch", "_bi_layer_idx0", "_bi_layer_idx1"):
+        assert torch.equal(getattr(A, k), getattr(B, k))
+    assert A.num_graphs == 6 and A.x.shape[1] == 2 and A.edge_attr.shape[1] == 2
+    # levels are computed on the AST edges only (edge_attr[:,0] == 0), like ogb/io/read_graph_pyg.py:51
+    ast = A.edge_index[:, A.edge_attr[:, 0] == 0]
+    counts = D.graph_node_counts(A)
+    off = 0
+    for g, n in enumerate(counts):
+        m = (ast[0] >= off) & (ast[0] < off + n)
+        ei = (ast[:, m] - off).numpy()
+        assert np.array_equal(O.top_sort(ei, int(n)).numpy(), A._bi_layer_idx0[off:off + n].numpy())
+        assert np.array_equal(O.top_sort(ei[::-1].copy(), int(n)).numpy(), A._bi_layer_idx1[off:off + n].numpy())
+        off += int(n)
+    # next-token edges exist and some violate the level order (they read zeros but keep softmax mass)
+    nt = A.edge_index[:, A.edge_attr[:, 0] == 1]
+    assert nt.shape[1] > 0 and bool((A._bi_layer_idx0[nt[0]] >= A._bi_layer_idx0[nt[1]]).any())
+
+
+def test_select_and_split_roundtrip():
+    B = D.make_code2_batch(9, 3)
+    parts = D.split_batch(B, [range(0, 4), range(4, 9)])
+    assert sum(p.num_graphs for p in parts) == 9 and sum(p.x.shape[0] for p in parts) == B.x.shape[0]
+    sub = D.select_graphs(B, [2, 5])
+    cnt = D.graph_node_counts(B)
+    assert sub.x.shape[0] == cnt[2] + cnt[5] and int(sub.edge_index.max()) < sub.x.shape[0]
+    assert torch.equal(sub._bi_layer_index0, torch.arange(sub.x.shape[0]))
+
+
+def test_shard_ranges_cover_and_balance():
+    rng = np.random.default_rng(0)
+    for w in (1, 2, 4, 8):
+        nodes = rng.integers(11, 400, size=64)
+        rs = D.shard_graph_ranges(nodes, w)
+        assert len(rs) == w and rs[0].start == 0 and rs[-1].stop == 64
+        assert all(rs[k].stop == rs[k + 1].start for k in range(w - 1))
+        loads = [int(nodes[r.start:r.stop].sum()) for r in rs]
+        assert max(loads) - min(loads) <= 2 * int(nodes.max())       # contiguous node-balanced split (tg/dataloader.py:17-27)
+
+
+def test_dvae_row_decoders():
+    G = D.make_random_dvae_batch(5, 11, "NA")
+    assert G.x.shape == (40, 8) and G.bi_layer_index.shape == (2, 2, 40)
+    assert torch.equal(G.bi_layer_index[0][1], torch.arange(40))
+    for g in range(5):                                              # ENAS rows: a chain 0->1->...->7 plus skip edges: 8 levels
+        assert torch.equal(G.bi_layer_index[0][0][8 * g:8 * g + 8], torch.arange(8))
+    Gb = D.make_random_dvae_batch(4, 12, "BN")
+    assert Gb.x.shape == (40, 10)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B = D.make_code2_batch(10, 21)
+        mine, rng = sharding.shard_for_rank(B)
+        # (1) every rank derives the same partition without communication; shards tile the batch
+        sizes = torch.tensor([mine.num_graphs, mine.x.shape[0]])
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        assert sum(int(s[0]) for s in allsz) == 10 and sum(int(s[1]) for s in allsz) == B.x.shape[0]
+        # (2) a per-graph "readout" computed on the shard, gathered in rank order == the same on the whole batch
+        def per_graph(b):
+            return torch.zeros(b.num_graphs, 3).index_add(0, b.batch, torch.stack([b.x[:, 0].float(), b.x[:, 1].float(),
+                                                                                    b._bi_layer_idx0.float()], 1))
+        full = per_graph(B)
+        got = sharding.gather_rows(per_graph(mine), [int(s[0]) for s in allsz])
+        assert torch.equal(got, full)
+        # (3) gradient all-reduce: sum of shard gradients of a sum-loss == full-batch gradient
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(3, 2)
+        lin(per_graph(mine)).sum().backward()
+        n = sharding.allreduce_gradients(lin.parameters())
+        ref = torch.nn.Linear(3, 2)
+        ref.load_state_dict(lin.state_dict())
+        ref(full).sum().backward()
+        assert n == 8 and torch.allclose(lin.weight.grad, ref.weight.grad, atol=1e-4) and torch.allclose(lin.bias.grad, ref.bias.grad)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_sharding_and_gradient_allreduce():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: 1, 1: 1}
