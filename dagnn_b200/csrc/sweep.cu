@@ -60,6 +60,7 @@ struct LayP {
   float* alpha;         // [E] scratch: softmax weights of tiles whose edge list exceeds the shared-memory cache
   float* skp;           // [N][nskp] partial key scores wk . h over 16-unit groups, written with every state row
 };
+constexpr int kHeavy = 2;                                // rows with more in-edges get their aggregate precomputed per tile
 struct SweepP {
   int dirs, layers, H, Hq, nvid, use_ea;
   int Din0, nci0, ncih;       // layer-0 input width, 64-k chunks of the layer-0 input / of a hidden-width operand
@@ -68,6 +69,7 @@ struct SweepP {
   const float* X;             // [N, ldx] node order (rows through perm)
   const int* summary;         // [0] number of levels of direction 0, [2] schedule status
   unsigned int* bar;          // grid barrier counter (zeroed by the launcher)
+  float* heavy;               // [grid][kMaxRows][Hq] per-CTA scratch: aggregates m_v of the tile's high-in-degree rows
   long long* trace;           // optional [steps][256][16] clock64 stamps, nullptr = off
   DirP dir[DAGNN_MAX_DIRS];
   LayP lay[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
@@ -76,14 +78,17 @@ struct SweepP {
 struct Seg {
   int pos0, n, ntile, base;
 };
+struct StepTab {
+  Seg seg[kMaxSeg];
+  int U, nst;                 // units per tile, 128-row sub-tiles per tile
+};
 struct SmemTail {
   float alpha[kEdgeCap];
   int col[kEdgeCap];
   int rp[kMaxRows + 4];
   int nidx[kMaxRows];
-  Seg seg[kMaxSeg];
+  StepTab tab[2];             // this step's and the next step's segment tables
   float bias[5][64];          // b_r, b_z, b_in, b_hn, wk of the tile's units
-  int info[4];                // units per tile, sub-tiles per tile
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
   uint32_t tmem_slot;
 };
@@ -168,7 +173,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
   const bool level0 = T.level0 != 0;
   const bool trc = tr != nullptr && tid == 0;
 #ifdef DAGNN_TRACE_FINE
-  long long t_pre = 0, t_wait = 0, t_build = 0, t_hand = 0, t0 = 0;
+  long long t_pre = 0, t_wait = 0, t_build = 0, t_hand = 0, t_comb = 0, t_pref = 0, t0 = 0;
   if (trc) t0 = clock64();
 #define TRC_ACC(var) if (trc) { const long long t1 = clock64(); var += t1 - t0; t0 = t1; }
 #else
@@ -232,6 +237,38 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
         const float inv = 1.f / (sum + 1e-16f);
         for (int k = i0; k < i1; ++k) S.alpha[k] = (S.col[k] < T.pos0) ? expf(S.alpha[k] - mx) * inv : 0.f;
       }
+      // rows with many in-edges: one warp per row aggregates m_v = sum_e alpha_e h_e over the full width with four
+      // predecessor rows in flight and parks it in this CTA's scratch; the row then looks like a single in-edge of
+      // weight 1 to the operand builders (whose per-item gather is serial over edges)
+      builders_sync();
+      float* scr = P.heavy + (size_t)blockIdx.x * kMaxRows * Hq;
+      for (int r = warp; r < T.nrows; r += kBuilderWarps) {
+        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
+        if (i1 - i0 <= kHeavy) continue;                 // warp-uniform
+        for (int kb = 4 * lane; kb < Hq; kb += 128) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = i0; k < i1; k += 4) {
+            float w[4];
+            float4 h[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              w[t] = (k + t < i1) ? S.alpha[k + t] : 0.f;
+              h[t] = (w[t] != 0.f) ? ldcg4(Hcur + (size_t)S.col[k + t] * ldh + kb) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              acc.x = fmaf(w[t], h[t].x, acc.x); acc.y = fmaf(w[t], h[t].y, acc.y);
+              acc.z = fmaf(w[t], h[t].z, acc.z); acc.w = fmaf(w[t], h[t].w, acc.w);
+            }
+          }
+          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = acc;
+        }
+        __syncwarp();
+        for (int k = i0 + lane; k < i1; k += 32) {
+          S.alpha[k] = (k == i0) ? 1.f : 0.f;
+          if (k == i0) S.col[k] = ~r;                    // negative: row r of the scratch
+        }
+      }
     } else if (tid < T.nrows) {
       // edge list larger than the cache: row-serial, softmax weights in global scratch. Only FINAL weights are stored —
       // the CTAs of the other unit tiles of these rows write the same values to the same addresses concurrently.
@@ -268,14 +305,20 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
   const int own = (T.ut * U) >> 6;                       // hidden chunk that covers the tile's own units
   const int nitems = T.nchunks * T.nst;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* scr_ = P.heavy + (size_t)blockIdx.x * kMaxRows * Hq;
 
+  // row groups (of kRStride rows) a sub-tile really has: the tail levels hold a handful of rows per tile
+  auto groups_of = [&](int st) { return min(kNR, (min(128, T.nrows - st * 128) + kRStride - 1) / kRStride); };
   auto prefetch = [&](int it, Pre& R) {
-#pragma unroll
-    for (int x = 0; x < kNR; ++x)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) { R.v[x][k][0] = z4; R.v[x][k][1] = z4; R.w[x][k] = 0.f; }
     if (it >= nitems) return;
     const int c = it / T.nst, st = it - c * T.nst;
+    const int nx = groups_of(st);
+#pragma unroll
+    for (int x = 0; x < kNR; ++x)
+      if (x < nx) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { R.v[x][k][0] = z4; R.v[x][k][1] = z4; R.w[x][k] = 0.f; }
+      }
     const int ra = st * 128 + r0;
     if (c < T.nci) {
       const int k0 = c * tc::KC16 + 8 * c8;
@@ -284,7 +327,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
 #pragma unroll
       for (int x = 0; x < kNR; ++x) {
         const int r = ra + kRStride * x;
-        if (r >= T.nrows) continue;
+        if (x >= nx || r >= T.nrows) continue;
         const float* src = inp + (size_t)S.nidx[r] * ld_inp + k0;
         R.w[x][0] = 1.f;
         if (vec_in) {
@@ -305,7 +348,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
 #pragma unroll
       for (int x = 0; x < kNR; ++x) {
         const int r = ra + kRStride * x;
-        if (r >= T.nrows) continue;
+        if (x >= nx || r >= T.nrows) continue;
         const int e0 = S.rp[r], e1 = S.rp[r + 1];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -313,7 +356,8 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
             const float w = alpha_of(e0 + k);
             R.w[x][k] = w;
             if (w != 0.f) {
-              const float* hr = Hcur + (size_t)col_of(e0 + k) * ldh + k0;
+              const int cc = col_of(e0 + k);
+              const float* hr = (cc >= 0 ? Hcur + (size_t)cc * ldh : scr_ + (size_t)(~cc) * Hq) + k0;
               R.v[x][k][0] = ldcg4(hr);
               if (two) R.v[x][k][1] = ldcg4(hr + 4);
             }
@@ -334,14 +378,18 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
     unsigned char* A_lo = A_hi + 128 * tc::ROW_BYTES;
     // combine the prefetched sources, then put the next item's loads in flight before anything else
     float x[kNR][8];
+    const int nx = groups_of(st);
 #pragma unroll
     for (int q = 0; q < kNR; ++q) {
+      if (q >= nx) continue;
       const float w0 = R.w[q][0], w1 = R.w[q][1];
       const float4 a0 = R.v[q][0][0], a1 = R.v[q][0][1], b0 = R.v[q][1][0], b1 = R.v[q][1][1];
       x[q][0] = fmaf(w1, b0.x, w0 * a0.x); x[q][1] = fmaf(w1, b0.y, w0 * a0.y); x[q][2] = fmaf(w1, b0.z, w0 * a0.z); x[q][3] = fmaf(w1, b0.w, w0 * a0.w);
       x[q][4] = fmaf(w1, b1.x, w0 * a1.x); x[q][5] = fmaf(w1, b1.y, w0 * a1.y); x[q][6] = fmaf(w1, b1.z, w0 * a1.z); x[q][7] = fmaf(w1, b1.w, w0 * a1.w);
     }
+    TRC_ACC(t_comb)
     prefetch(it + 1, R);
+    TRC_ACC(t_pref)
     const int ra = st * 128 + r0;
     if (c >= T.nci) {                                    // rows with more than two in-edges: the rest, two edges in flight
       const int k0 = hperm(c - T.nci, nch, own) * tc::KC16 + 8 * c8;
@@ -350,7 +398,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
 #pragma unroll
         for (int q = 0; q < kNR; ++q) {
           const int r = ra + kRStride * q;
-          if (r >= T.nrows) continue;
+          if (q >= nx || r >= T.nrows) continue;
           const int e1 = S.rp[r + 1];
           for (int e = S.rp[r] + 2; e < e1; e += 2) {
             float w[2];
@@ -379,7 +427,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
     TRC_ACC(t_wait)
 #pragma unroll
     for (int q = 0; q < kNR; ++q)                                           // rows beyond the tile: D rows nobody reads
-      if (ra + kRStride * q < T.nrows) tc::store_split8(A_hi, A_lo, r0 + kRStride * q, c8, x[q]);
+      if (q < nx && ra + kRStride * q < T.nrows) tc::store_split8(A_hi, A_lo, r0 + kRStride * q, c8, x[q]);
     TRC_ACC(t_build)
     tc::fence_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncwarp();
@@ -388,7 +436,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
   }
   if (trc) tr[1] = clock64();
 #ifdef DAGNN_TRACE_FINE
-  if (trc) { tr[8] = t_pre; tr[9] = t_wait; tr[10] = t_build; tr[11] = t_hand; }
+  if (trc) { tr[8] = t_pre; tr[9] = t_wait; tr[10] = t_build; tr[11] = t_hand; tr[12] = t_comb; tr[13] = t_pref; }
 #endif
 
   // ---------------- epilogue ----------------
@@ -474,44 +522,72 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
 struct RingState {
   uint32_t full_par, empty_par, pending;     // bit s: parity of the next wait on b_full[s] / b_empty[s]; commit outstanding
   uint32_t next;                             // next stage to fill
+  uint32_t pre, pre_first;                   // chunks of the upcoming tile already in flight, stage of its chunk 0
+  int U;                                     // units per tile the ring is currently laid out for (2 x 48 KB or 8 x 12 KB stages)
 };
+struct BSrc {                                // where the weight chunks of a tile come from, and the ring geometry for its U
+  const unsigned char* img;
+  uint32_t bstage;
+  int nbs, nci, nch, own;
+};
+__device__ __forceinline__ BSrc make_bsrc(const SweepP& P, const Tile& T, int U) {
+  const LayP& Lp = P.lay[T.d][T.i];
+  BSrc b;
+  b.nbs = (U == 64) ? 2 : 8;
+  b.bstage = 2u * 3u * (uint32_t)U * tc::ROW_BYTES;                         // hi + lo tile of 3U rows
+  const int nc_all = ((T.i == 0) ? P.nci0 : P.ncih) + P.ncih;               // chunks per unit block in the image
+  b.img = reinterpret_cast<const unsigned char*>(U == 64 ? Lp.img64 : Lp.img16) + (size_t)T.ut * nc_all * b.bstage;
+  b.nci = T.nci; b.nch = T.nchunks - T.nci; b.own = (T.ut * U) >> 6;
+  return b;
+}
+// weight chunk at processing position c of a tile -> next ring stage
+__device__ __forceinline__ void ring_load(const BSrc& b, int c, unsigned char* Bs, SmemTail& S, RingState& R) {
+  if (c >= b.nci) c = b.nci + hperm(c - b.nci, b.nch, b.own);
+  const uint32_t s = R.next;
+  R.next = (s + 1 == (uint32_t)b.nbs) ? 0u : s + 1;
+  if (R.pending >> s & 1u) {                         // MMAs that read this stage must be done
+    mbar_wait(&S.b_empty[s], R.empty_par >> s & 1u);
+    R.empty_par ^= 1u << s;
+    R.pending &= ~(1u << s);
+  }
+  mbar_expect_tx(&S.b_full[s], b.bstage);
+  bulk_g2s(Bs + (size_t)s * b.bstage, b.img + (size_t)c * b.bstage, b.bstage, &S.b_full[s]);
+}
+
+// the ring geometry changes with U: every stage must be drained before the region is re-cut
+__device__ __forceinline__ void ring_set_geometry(int U, SmemTail& S, RingState& R) {
+  if (R.U == U) return;
+  for (uint32_t q = 0; q < (uint32_t)kNBBar; ++q)
+    if (R.pending >> q & 1u) {
+      mbar_wait(&S.b_empty[q], R.empty_par >> q & 1u);
+      R.empty_par ^= 1u << q;
+      R.pending &= ~(1u << q);
+    }
+  R.next = 0;
+  R.U = U;
+}
 
 __device__ __forceinline__ void issuer_tile(const SweepP& P, const Tile& T, int U, unsigned char* As, unsigned char* Bs, SmemTail& S,
-                                            uint32_t tmem, uint32_t ja, RingState& R, long long* tr) {
-  const LayP& Lp = P.lay[T.d][T.i];
+                                            uint32_t tmem, uint32_t ja, RingState& R, long long* tr, const Tile* nextT, int nextU) {
   long long i_b = 0, i_a = 0, i_issue = 0, t0 = tr ? clock64() : 0;
-  const int nbs = (U == 64) ? 2 : 8;
-  const uint32_t bstage = 2u * 3u * (uint32_t)U * tc::ROW_BYTES;           // hi + lo tile of 3U rows
-  const int nc_all = ((T.i == 0) ? P.nci0 : P.ncih) + P.ncih;               // chunks per unit block in the image
-  const unsigned char* img = reinterpret_cast<const unsigned char*>(U == 64 ? Lp.img64 : Lp.img16) + (size_t)T.ut * nc_all * bstage;
+  const BSrc b = make_bsrc(P, T, U);
+  const int nbs = b.nbs;
   const uint32_t idesc3 = tc::instr_desc_f16(128, 3 * U), idesc2 = tc::instr_desc_f16(128, 2 * U), idesc1 = tc::instr_desc_f16(128, U);
 
-  const int own = (T.ut * U) >> 6;
-  auto load_B = [&](int c) -> uint32_t {               // weight chunk at processing position c -> next ring stage
-    if (c >= T.nci) c = T.nci + hperm(c - T.nci, T.nchunks - T.nci, own);
-    const uint32_t s = R.next;
-    R.next = (s + 1 == (uint32_t)nbs) ? 0u : s + 1;
-    if (R.pending >> s & 1u) {                         // MMAs that read this stage must be done
-      mbar_wait(&S.b_empty[s], R.empty_par >> s & 1u);
-      R.empty_par ^= 1u << s;
-      R.pending &= ~(1u << s);
-    }
-    mbar_expect_tx(&S.b_full[s], bstage);
-    bulk_g2s(Bs + (size_t)s * bstage, img + (size_t)c * bstage, bstage, &S.b_full[s]);
-    return s;
-  };
-
-  // chunk c sits in stage (first + c) % nbs
-  const uint32_t first = R.next;
+  // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
+  // was still computing, or before the grid barrier)
+  if (R.pre == 0) ring_set_geometry(U, S, R);
+  const uint32_t first = R.pre ? R.pre_first : R.next;
   const int npre = min(nbs, T.nchunks);
-  for (int c = 0; c < npre; ++c) load_B(c);
+  for (int c = (int)R.pre; c < npre; ++c) ring_load(b, c, Bs, S, R);
+  R.pre = 0;
 #pragma unroll 1
   for (int c = 0; c < T.nchunks; ++c) {
     const uint32_t s = (first + (uint32_t)c) % (uint32_t)nbs;
     mbar_wait(&S.b_full[s], R.full_par >> s & 1u);
     R.full_par ^= 1u << s;
     if (tr) { const long long t1 = clock64(); i_b += t1 - t0; t0 = t1; }
-    const uint32_t sb = smem_u32(Bs + (size_t)s * bstage);
+    const uint32_t sb = smem_u32(Bs + (size_t)s * b.bstage);
     const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + 3u * (uint32_t)U * tc::ROW_BYTES);
 #pragma unroll 1
     for (int st = 0; st < T.nst; ++st) {
@@ -548,10 +624,82 @@ __device__ __forceinline__ void issuer_tile(const SweepP& P, const Tile& T, int 
     tc::commit(&S.b_empty[s]);
     R.pending |= 1u << s;
     // refill: chunk c + nbs - 1 goes where chunk c - 1 was (its MMAs precede the ones just issued)
-    if (c >= 1 && c + nbs - 1 < T.nchunks) load_B(c + nbs - 1);
+    if (c >= 1 && c + nbs - 1 < T.nchunks) ring_load(b, c + nbs - 1, Bs, S, R);
   }
   tc::commit(&S.acc_full);
-  if (tr) { tr[12] = i_b; tr[13] = i_a; tr[14] = i_issue; tr[15] = T.nchunks * T.nst; }
+  if (tr) { tr[14] = i_a; tr[15] = i_issue; (void)i_b; }
+  // weights are constants: put the first chunks of this CTA's NEXT tile in flight now — they land while the current
+  // accumulators drain, the epilogue runs and (for the first tile of the next step) the grid barrier is crossed
+  if (nextT) {
+    ring_set_geometry(nextU, S, R);
+    const BSrc nb = make_bsrc(P, *nextT, nextU);
+    R.pre_first = R.next;
+    const int n2 = min(nb.nbs, nextT->nchunks);
+    for (int c = 0; c < n2; ++c) ring_load(nb, c, Bs, S, R);
+    R.pre = (uint32_t)n2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// step tables: the segments (d, i, l = s - i) of a wavefront step, their tiling and this CTA's share of the tiles
+// ------------------------------------------------------------------------------------------------------------
+struct TileIt { int q, t; };
+
+__device__ __forceinline__ bool tile_advance(const StepTab& tb, int nseg, int rank, int G, TileIt& it) {
+  if (it.t >= 0) it.t += G;
+  while (it.q < nseg) {
+    const Seg g = tb.seg[it.q];
+    if (it.t < 0) it.t = ((rank - g.base) % G + G) % G;     // my tiles of a segment: global ids base + t with (base + t) % G == rank
+    if (it.t < g.ntile) return true;
+    ++it.q;
+    it.t = -1;
+  }
+  return false;
+}
+__device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, int s, const TileIt& it) {
+  const Seg g = tb.seg[it.q];
+  const int NU = (tb.U == 64) ? P.NT : P.NG;
+  const int rows_per = 128 * tb.nst;
+  Tile T;
+  const int rt = it.t / NU;
+  T.d = it.q / P.layers; T.i = it.q - T.d * P.layers;
+  T.level0 = (s - T.i == 0); T.pos0 = g.pos0;
+  T.ut = it.t - rt * NU;
+  T.p0 = g.pos0 + rt * rows_per;
+  T.nrows = min(rows_per, g.n - rt * rows_per);
+  T.nst = (T.nrows + 127) >> 7;
+  T.nci = (T.i == 0) ? P.nci0 : P.ncih;
+  T.nchunks = T.nci + (T.level0 ? 0 : P.ncih);
+  return T;
+}
+// all threads; two __syncthreads inside
+__device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg, int G) {
+  const int tid = threadIdx.x;
+  if (tid < nseg) {
+    const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
+    Seg g = {0, 0, 0, 0};
+    if (l >= 0 && l < L) {
+      g.pos0 = P.dir[d].lvl_off[l];
+      g.n = max(0, P.dir[d].lvl_off[l + 1] - g.pos0);
+    }
+    tb.seg[tid] = g;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t64 = 0;
+    for (int q = 0; q < nseg; ++q) t64 += ceil_div(tb.seg[q].n, 128) * P.NT;
+    const int U = (4 * t64 >= G) ? 64 : 16;
+    const int nst = (U == 64 && t64 >= 2 * G) ? 2 : 1;
+    const int NU = (U == 64) ? P.NT : P.NG;
+    int base_ = 0;
+    for (int q = 0; q < nseg; ++q) {
+      tb.seg[q].ntile = ceil_div(tb.seg[q].n, 128 * nst) * NU;
+      tb.seg[q].base = base_;
+      base_ += tb.seg[q].ntile;
+    }
+    tb.U = U; tb.nst = nst;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ SweepP P) {
@@ -578,74 +726,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   const int L = ok ? P.summary[0] : 0;
   const int nsteps = ok ? L + P.layers - 1 : 0;
   const int nseg = P.dirs * P.layers;
-  const int G = (int)gridDim.x;
+  const int G = (int)gridDim.x, rank = (int)blockIdx.x;
   uint32_t ja = 0, ct = 0;
-  RingState R = {0u, 0u, 0u, 0u};
+  RingState R = {0u, 0u, 0u, 0u, 0u, 0u, 0};
   unsigned int nbar = 0;
+  if (nsteps > 0) build_step_table(P, S.tab[0], 0, L, nseg, G);
 
 #pragma unroll 1
   for (int s = 0; s < nsteps; ++s) {
     long long* tr = P.trace ? P.trace + ((size_t)s * 256 + blockIdx.x) * 16 : nullptr;
     if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; tr[8] = tr[9] = tr[10] = tr[11] = 0; }
-    // ---- the segments of this step and their tiling
-    if (tid < nseg) {
-      const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
-      Seg g = {0, 0, 0, 0};
-      if (l >= 0 && l < L) {
-        g.pos0 = P.dir[d].lvl_off[l];
-        g.n = max(0, P.dir[d].lvl_off[l + 1] - g.pos0);
-      }
-      S.seg[tid] = g;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t64 = 0;
-      for (int q = 0; q < nseg; ++q) t64 += ceil_div(S.seg[q].n, 128) * P.NT;
-      const int U = (4 * t64 >= G) ? 64 : 16;
-      const int nst = (U == 64 && t64 >= 2 * G) ? 2 : 1;
-      const int NU = (U == 64) ? P.NT : P.NG;
-      int base_ = 0;
-      for (int q = 0; q < nseg; ++q) {
-        S.seg[q].ntile = ceil_div(S.seg[q].n, 128 * nst) * NU;
-        S.seg[q].base = base_;
-        base_ += S.seg[q].ntile;
-      }
-      S.info[0] = U; S.info[1] = nst;
-    }
-    __syncthreads();
-    const int U = S.info[0], nst_max = S.info[1];
-    const int NU = (U == 64) ? P.NT : P.NG;
-    const int rows_per = 128 * nst_max;
-    R.next = 0;               // the ring geometry may change with U: every stage is drained at a step boundary
+    // the table of step s was built during step s - 1 (level offsets are constants); build the one of step s + 1 now so
+    // that the issuer can look across the grid barrier
+    const StepTab& tb = S.tab[s & 1];
+    StepTab& tbn = S.tab[(s + 1) & 1];
+    const bool has_next = s + 1 < nsteps;
+    if (has_next) build_step_table(P, tbn, s + 1, L, nseg, G);
+    const int U = tb.U;
     int my_tiles = 0;
+    TileIt it = {0, -1};
+    bool more = tile_advance(tb, nseg, rank, G, it);
 #pragma unroll 1
-    for (int q = 0; q < nseg; ++q) {
-      const Seg g = S.seg[q];
-      if (g.ntile == 0) continue;
-      const int d = q / P.layers, i = q - d * P.layers, l = s - i;
-      // my tiles of this segment: global tile ids base + t with (base + t) % G == blockIdx.x
-      int t = (((int)blockIdx.x - g.base) % G + G) % G;
-#pragma unroll 1
-      for (; t < g.ntile; t += G) {
-        Tile T;
-        const int rt = t / NU;
-        T.d = d; T.i = i; T.level0 = (l == 0); T.pos0 = g.pos0;
-        T.ut = t - rt * NU;
-        T.p0 = g.pos0 + rt * rows_per;
-        T.nrows = min(rows_per, g.n - rt * rows_per);
-        T.nst = (T.nrows + 127) >> 7;
-        T.nci = (i == 0) ? P.nci0 : P.ncih;
-        T.nchunks = T.nci + (T.level0 ? 0 : P.ncih);
-        if (warp < kBuilderWarps) builder_tile(P, T, U, As, S, tmem, ja, ct, my_tiles == 0 ? tr : nullptr);
-        else if (lane == 0) issuer_tile(P, T, U, As, Bs, S, tmem, ja, R, my_tiles == 0 ? tr : nullptr);
-        __syncwarp();
-        ja += (uint32_t)(T.nchunks * T.nst);
-        ct += 1;
-        ++my_tiles;
+    while (more) {
+      const Tile T = make_tile(P, tb, s, it);
+      more = tile_advance(tb, nseg, rank, G, it);
+      if (warp < kBuilderWarps) {
+        builder_tile(P, T, U, As, S, tmem, ja, ct, my_tiles == 0 ? tr : nullptr);
+      } else if (lane == 0) {
+        Tile N;
+        int nU = U;
+        bool hn = more;
+        if (more) N = make_tile(P, tb, s, it);
+        else if (has_next) {
+          TileIt it2 = {0, -1};
+          hn = tile_advance(tbn, nseg, rank, G, it2);
+          if (hn) { N = make_tile(P, tbn, s + 1, it2); nU = tbn.U; }
+        }
+        issuer_tile(P, T, U, As, Bs, S, tmem, ja, R, my_tiles == 0 ? tr : nullptr, hn ? &N : nullptr, nU);
       }
+      __syncwarp();
+      ja += (uint32_t)(T.nchunks * T.nst);
+      ct += 1;
+      ++my_tiles;
     }
-    if (tr && tid == 0) { tr[4] = clock64(); tr[6] = my_tiles; tr[7] = U | (rows_per << 8); }
-    if (s + 1 < nsteps) grid_barrier(P.bar, ++nbar * (unsigned int)G);
+    if (tr && tid == 0) { tr[4] = clock64(); tr[6] = my_tiles; tr[7] = U | ((128 * tb.nst) << 8); }
+    if (has_next) grid_barrier(P.bar, ++nbar * (unsigned int)G);
     if (tr && tid == 0) tr[5] = clock64();
   }
   tc::fence_before_sync();
@@ -658,11 +783,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
 using namespace dagnn;
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+constexpr int kMaxGrid = 160;     // CTAs (= SMs) the per-CTA scratch is sized for
+static size_t heavy_bytes(int H) { return align256((size_t)kMaxGrid * kMaxRows * round_up(H, 4) * sizeof(float)); }
 
 extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E) {
   if (dirs < 1 || dirs > DAGNN_MAX_DIRS || layers < 1 || layers > DAGNN_MAX_LAYERS || Din < 1 || H < 1 || N < 0 || E < 0) return 0;
   const size_t nskp = (size_t)round_up(ceil_div(H, 16), 4);
-  return 256 + (size_t)dirs * layers * (align256((size_t)N * nskp * sizeof(float)) + align256((size_t)E * sizeof(float)));
+  return 256 + heavy_bytes(H) + (size_t)dirs * layers * (align256((size_t)N * nskp * sizeof(float)) + align256((size_t)E * sizeof(float)));
 }
 extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)max_steps * 256 * 16 * sizeof(long long); }
 
@@ -692,6 +819,8 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   P.ldh = A->ldh; P.ldx = A->ldx; P.X = A->X; P.summary = S->summary; P.bar = static_cast<unsigned int*>(A->workspace);
   P.trace = static_cast<long long*>(A->trace);
   char* ws = static_cast<char*>(A->workspace) + 256;
+  P.heavy = reinterpret_cast<float*>(ws);
+  ws += heavy_bytes(H);
   const size_t skp_bytes = align256((size_t)S->N * P.nskp * sizeof(float)), alpha_bytes = align256((size_t)S->E * sizeof(float));
   for (int d = 0; d < dirs; ++d) {
     DAGNN_REQUIRE(S->perm[d] && S->rowptr[d] && S->lvl_off[d] && (S->E == 0 || S->col[d]), "sweep: schedule arrays");
@@ -724,7 +853,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
     if (!coop) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device has no cooperative launch");
     sm_count[dev] = n;
   }
-  const int G = sm_count[dev];
+  const int G = sm_count[dev] < kMaxGrid ? sm_count[dev] : kMaxGrid;
   DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 16, st));
   void* kargs[] = {(void*)&P};
   DAGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(G), dim3(kThreads), kargs, kSmemBytes, st));

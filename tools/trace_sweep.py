@@ -27,7 +27,7 @@ MHZ = 1965.0
 lo = sched.lvl_off_host
 print("all times in us. first tile of CTA 0: pre = rowptr + softmax weights, wait = free operand stage, build = gather+split+store, "
       "hand = proxy fence + arrive; issuer: wB = wait weights, wA = wait operands, iss = MMA issue")
-print("step | level sizes | U rows | tiles/CTA | build  acc  epi  rest (max over CTAs) | step || slowest CTA: pre wait build hand | wB wA iss #stg")
+print("step | level sizes | U rows | tiles/CTA | build  acc  epi  rest (max over CTAs) | step || slowest CTA: pre wait slow+store hand comb pref | wA iss")
 tot = 0
 for s in range(steps):
     t = tr[s].astype(np.float64)
@@ -40,9 +40,9 @@ for s in range(steps):
     tot += stepdur
     k = int(np.argmax(np.where(act, t[:, 4] - t[:, 0], -1))) if act.any() else 0     # slowest CTA of the step
     f = int(t[0, 7])
-    print("%3d | %12s | %2d %3d | %2d | %6.1f %6.1f %6.1f %7.1f | %7.1f || %5.1f %5.1f %5.1f %5.1f | %5.1f %5.1f %5.1f %3d" % (
+    print("%3d | %12s | %2d %3d | %2d | %6.1f %6.1f %6.1f %7.1f | %7.1f || %5.1f %5.1f %5.1f %5.1f %5.1f %5.1f | %5.1f %5.1f" % (
         s, n0, f & 255, f >> 8, int(t[:, 6].max()), g.max(), bw.max(), pm.max(), tl.max(), stepdur,
-        t[k, 8] / MHZ, t[k, 9] / MHZ, t[k, 10] / MHZ, t[k, 11] / MHZ, t[k, 12] / MHZ, t[k, 13] / MHZ, t[k, 14] / MHZ, int(t[k, 15])))
+        t[k, 8] / MHZ, t[k, 9] / MHZ, t[k, 10] / MHZ, t[k, 11] / MHZ, t[k, 12] / MHZ, t[k, 13] / MHZ, t[k, 14] / MHZ, t[k, 15] / MHZ))
     if len(sys.argv) > 2 and s == int(sys.argv[2]):       # per-CTA dump of one step
         for c in range(148):
             print("   cta %3d tiles %d | build %.1f acc %.1f epi %.1f rest %.1f | pre %.1f wait %.1f build %.1f hand %.1f | wB %.1f wA %.1f iss %.1f stg %d" % (
