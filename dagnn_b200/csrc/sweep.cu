@@ -61,6 +61,8 @@ struct LayP {
   float* skp;           // [N][nskp] partial key scores wk . h over 16-unit groups, written with every state row
 };
 constexpr int kHeavy = 2;                                // rows with more in-edges get their aggregate precomputed per tile
+constexpr int kVeryHeavy = 24;                           // ... by the whole CTA instead of one warp
+constexpr int kMaxVH = 16;
 struct SweepP {
   int dirs, layers, H, Hq, nvid, use_ea;
   int Din0, nci0, ncih;       // layer-0 input width, 64-k chunks of the layer-0 input / of a hidden-width operand
@@ -89,6 +91,8 @@ struct SmemTail {
   int nidx[kMaxRows];
   StepTab tab[2];             // this step's and the next step's segment tables
   float bias[5][64];          // b_r, b_z, b_in, b_hn, wk of the tile's units
+  int vh[kMaxVH];             // rows of the tile whose edge list the whole CTA aggregates
+  int nvh;
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
   uint32_t tmem_slot;
 };
@@ -237,37 +241,91 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
         const float inv = 1.f / (sum + 1e-16f);
         for (int k = i0; k < i1; ++k) S.alpha[k] = (S.col[k] < T.pos0) ? expf(S.alpha[k] - mx) * inv : 0.f;
       }
-      // rows with many in-edges: one warp per row aggregates m_v = sum_e alpha_e h_e over the full width with four
-      // predecessor rows in flight and parks it in this CTA's scratch; the row then looks like a single in-edge of
-      // weight 1 to the operand builders (whose per-item gather is serial over edges)
+      // rows with many in-edges: their aggregate m_v = sum_e alpha_e h_e is computed once per tile over the full width
+      // and parked in this CTA's scratch; the row then looks like a single in-edge of weight 1 to the operand builders
+      // (whose per-item gather is serial over edges). Up to kVeryHeavy in-edges: one warp per row, four predecessor
+      // rows x 256 columns in flight; beyond: the whole CTA splits the edge list of the row, partials meet in shared
+      // memory (the operand stages are idle during the pre-phase).
+      if (tid == 0) S.nvh = 0;
       builders_sync();
       float* scr = P.heavy + (size_t)blockIdx.x * kMaxRows * Hq;
-      for (int r = warp; r < T.nrows; r += kBuilderWarps) {
-        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
-        if (i1 - i0 <= kHeavy) continue;                 // warp-uniform
-        for (int kb = 4 * lane; kb < Hq; kb += 128) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int k = i0; k < i1; k += 4) {
-            float w[4];
-            float4 h[4];
+      auto agg_edges = [&](int kb, int k0, int k1, int kstep, float4& acc0, float4& acc1) {
+        const bool two = kb + 128 < Hq;
+        for (int k = k0; k < k1; k += 4 * kstep) {
+          float w[4];
+          float4 h0[4], h1[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              w[t] = (k + t < i1) ? S.alpha[k + t] : 0.f;
-              h[t] = (w[t] != 0.f) ? ldcg4(Hcur + (size_t)S.col[k + t] * ldh + kb) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              acc.x = fmaf(w[t], h[t].x, acc.x); acc.y = fmaf(w[t], h[t].y, acc.y);
-              acc.z = fmaf(w[t], h[t].z, acc.z); acc.w = fmaf(w[t], h[t].w, acc.w);
+          for (int t = 0; t < 4; ++t) {
+            const int kk = k + t * kstep;
+            w[t] = (kk < k1) ? S.alpha[kk] : 0.f;
+            h0[t] = make_float4(0.f, 0.f, 0.f, 0.f); h1[t] = h0[t];
+            if (w[t] != 0.f) {
+              const float* hr = Hcur + (size_t)S.col[kk] * ldh + kb;
+              h0[t] = ldcg4(hr);
+              if (two) h1[t] = ldcg4(hr + 128);
             }
           }
-          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = acc;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            acc0.x = fmaf(w[t], h0[t].x, acc0.x); acc0.y = fmaf(w[t], h0[t].y, acc0.y);
+            acc0.z = fmaf(w[t], h0[t].z, acc0.z); acc0.w = fmaf(w[t], h0[t].w, acc0.w);
+            acc1.x = fmaf(w[t], h1[t].x, acc1.x); acc1.y = fmaf(w[t], h1[t].y, acc1.y);
+            acc1.z = fmaf(w[t], h1[t].z, acc1.z); acc1.w = fmaf(w[t], h1[t].w, acc1.w);
+          }
         }
-        __syncwarp();
-        for (int k = i0 + lane; k < i1; k += 32) {
+      };
+      auto mark_row = [&](int r, int i0, int i1, int first_lane_k) {       // one warp: row r now reads scratch row r
+        for (int k = i0 + first_lane_k; k < i1; k += 32) {
           S.alpha[k] = (k == i0) ? 1.f : 0.f;
           if (k == i0) S.col[k] = ~r;                    // negative: row r of the scratch
         }
+      };
+      const bool vh_ok = (size_t)kBuilderWarps * Hq * sizeof(float) <= (size_t)kNAS * kAStageBytes;
+      for (int r = warp; r < T.nrows; r += kBuilderWarps) {
+        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
+        if (i1 - i0 <= kHeavy) continue;                 // warp-uniform
+        if (vh_ok && i1 - i0 > kVeryHeavy) {
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(&S.nvh, 1);
+          slot = __shfl_sync(0xffffffffu, slot, 0);
+          if (slot < kMaxVH) {
+            if (lane == 0) S.vh[slot] = r;
+            continue;
+          }
+        }
+        for (int kb = 4 * lane; kb < Hq; kb += 256) {
+          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+          agg_edges(kb, i0, i1, 1, acc0, acc1);
+          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = acc0;
+          if (kb + 128 < Hq) *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb + 128) = acc1;
+        }
+        __syncwarp();
+        mark_row(r, i0, i1, lane);
+      }
+      builders_sync();
+      const int nvh = min(S.nvh, kMaxVH);
+      float* part = reinterpret_cast<float*>(As);        // [kBuilderWarps][Hq] partial aggregates
+      for (int v = 0; v < nvh; ++v) {
+        const int r = S.vh[v];
+        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
+        for (int kb = 4 * lane; kb < Hq; kb += 256) {
+          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+          agg_edges(kb, i0 + warp, i1, kBuilderWarps, acc0, acc1);
+          *reinterpret_cast<float4*>(part + (size_t)warp * Hq + kb) = acc0;
+          if (kb + 128 < Hq) *reinterpret_cast<float4*>(part + (size_t)warp * Hq + kb + 128) = acc1;
+        }
+        builders_sync();
+        for (int kb = 4 * tid; kb < Hq; kb += 4 * kBuilders) {
+          float4 a = *reinterpret_cast<const float4*>(part + kb);
+#pragma unroll
+          for (int w = 1; w < kBuilderWarps; ++w) {
+            const float4 b = *reinterpret_cast<const float4*>(part + (size_t)w * Hq + kb);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = a;
+        }
+        if (warp == 0) mark_row(r, i0, i1, lane);
+        builders_sync();
       }
     } else if (tid < T.nrows) {
       // edge list larger than the cache: row-serial, softmax weights in global scratch. Only FINAL weights are stored —
