@@ -168,6 +168,16 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep launch from the committed `ncu --set full` capture
+    (profiles/traffic.json: bytes per launch, keyed by workload) or None."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(j[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -181,11 +191,22 @@ def measured_peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_baseline(p, B, wl, budget_s=25.0):
     """oracle port on this box's host cores: one untimed warm-up on a small slice, then full-batch forwards until
     ~budget_s is spent (at least 1, at most 5); graphs/s = graphs / median."""
     from dagnn_b200 import data as D
     ng = int(B.num_graphs)
+    use_all_host_threads()
     with torch.no_grad():
         oracle_forward(p, D.select_graphs(B, range(min(4, ng))), wl)
         ts, t_all = [], time.perf_counter()
@@ -208,6 +229,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     from dagnn_b200 import data as D
+    use_all_host_threads()
     B = build_workload(wl, world)
     m = build_module(wl)
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -383,7 +405,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_sweep (persistent level sweep, %d launch per forward)" % sweep_launches, "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "algorithmic_bytes_per_sweep": int(alg_bytes),
                          "sweep_ms": ms_sweep / args.steps, "gathered_edges": e_prime,
                          "gate_gemm_tflops_fp32": flops * args.steps / (ms_sweep * 1e-3) / 1e12},

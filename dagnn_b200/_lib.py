@@ -19,7 +19,7 @@ HEADERS = ["common.cuh", "tc.cuh"]
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 vp = C.c_void_p
 
@@ -36,10 +36,10 @@ class DagnnSchedule(C.Structure):
 
 class DagnnPackLayout(C.Structure):
     _fields_ = [
-        ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32), ("Kin64", C.c_int32), ("Kh64", C.c_int32),
-        ("NG", C.c_int32), ("NT", C.c_int32), ("HP", C.c_int32),
+        ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32), ("first_layer", C.c_int32), ("last_layer", C.c_int32),
+        ("Hq", C.c_int32), ("Mc", C.c_int32), ("Kin64", C.c_int32), ("Kh64", C.c_int32), ("HP", C.c_int32),
         ("bias_off", C.c_int64), ("wk_off", C.c_int64), ("attnc_off", C.c_int64), ("vidk_off", C.c_int64),
-        ("img16_off", C.c_int64), ("img64_off", C.c_int64), ("total_floats", C.c_int64),
+        ("imgx_off", C.c_int64), ("imgh_off", C.c_int64), ("total_floats", C.c_int64),
     ]
 
 
@@ -71,8 +71,8 @@ EXPORTS = {
     "dagnn_embed_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp]),
     "dagnn_schedule_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "dagnn_schedule_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DagnnSchedule), vp, C.c_size_t, vp]),
-    "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),
-    "dagnn_pack_params_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(DagnnPackLayout), vp, vp]),
+    "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),
+    "dagnn_pack_params_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.POINTER(DagnnPackLayout), vp, vp]),
     "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
     "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),

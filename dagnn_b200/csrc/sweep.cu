@@ -1,26 +1,25 @@
-// The DAGNN level sweep as ONE persistent cooperative kernel (one CTA per SM, one grid barrier per wavefront step),
-// gate GEMM on the 5th-generation tensor cores.
+// The DAGNN level sweep as ONE persistent cooperative kernel (one CTA per SM), "project, then aggregate".
 //
-// Wavefront step s runs every (direction d, layer i, level l) with l + i == s: (l, i) depends on (l, i-1) [its
-// input rows] and on (< l, i) [predecessor states], both finished in earlier steps. The sequential depth is
-// L + layers - 1 grid barriers instead of L * layers * dirs kernel chains, and nothing on the host depends on the
-// level sizes: level offsets and the level count are read from device memory (no host sync in a forward).
+// Algebra (exact; only the summation order changes — DESIGN.md §3.2): the GRU cell of layer i at node v needs
+//   W_ih^i inp_v   and   W_hh^i m_v,   m_v = sum_e alpha_e h^i_{j(e)}   (alpha = softmax of the separable attention score).
+// Both are linear, so  W_hh^i m_v = sum_e alpha_e (W_hh^i h^i_j)  and  inp_v = h^{i-1}_v  (or x_v for i = 0):
+//   projection  P^i_j  = W_hh^i h^i_j      — once per node, when its state is produced, for ALL its future successors;
+//   projection  Gi^i_v = W_ih^i h^{i-1}_v  — once per node (Gi^0 = W_ih^0 x_v for all nodes before the first level).
+// h^i_j is the operand of both P^i and Gi^{i+1}: ONE dense GEMM over the contiguous, just-written rows of a level
+// ([rows, H] x [H, 6H], no gather, no attention inside the GEMM) on the 5th-generation tensor cores, and the irregular
+// part (CSR gather, softmax, weighted sum, gate math) becomes a bandwidth-bound pass with one warp per node that
+// never touches a weight matrix.
 //
-// Work unit = tile (d, i, l, up to 256 consecutive positions of the level, U = 16 or 64 hidden units); the tiles of a
-// step are dealt round-robin to the CTAs; U = 64 when that still fills the grid, else 16 (latency-bound tail levels).
-// Warp roles: 16 builder/epilogue warps + 1 issuer warp.
-//   builders, pre-phase : one thread per row turns the in-edge scores into softmax weights alpha_e. Scores are scalar
-//                         gathers: s_e = sum_j skp[nbr][j] (+ edge-type / vertex-id terms) — every producer of a state
-//                         row also writes the partial key scores wk . h over 16-unit groups (separable attention score).
-//   builders, main loop : per 64-wide k chunk and 128-row sub-tile, build the A operand [128, 64] (input rows, or
-//                         m_v = sum_e alpha_e h_e for that k range) as fp16 hi / lo tiles straight into swizzled shared
-//                         memory (the aggregate never goes back to HBM), 2-stage ring handed over by mbarriers.
-//   issuer              : streams the pre-swizzled hi/lo weight image of the tile's units chunk by chunk with
-//                         cp.async.bulk (UBLKCP) into a ring, issues 4 k-steps x 3 products of tcgen05.mma kind::f16
-//                         (M = 128, N = 3U) per operand stage into TMEM, tcgen05.commit frees the stages.
-//   builders, epilogue  : tcgen05.ld of [n_in | r | z | n_hid], sigmoid/tanh/blend in registers, state row and
-//                         key-score partial stored.
-// States written in one step are read in later steps by OTHER CTAs: all state reads use ld.global.cg (L2), the
+// Wavefront step s runs every (direction d, layer i, level l) with l + i == s in two phases separated by grid barriers:
+//   gate phase : one warp per node of the step's segments: softmax weights of its in-edges from the key scores sk[j]
+//                (scalar gathers), a = Gi^i_v + sum_e alpha_e P^i_j, m_v = sum_e alpha_e h^i_j, GRU pointwise,
+//                h^i_v and sk[v] = wk . h^i_v stored. Level 0: no in-edges are read (hidden = 0).
+//   proj phase : tiles of <= 256 of the rows just produced x 64..256 output columns, dealt round-robin to the CTAs:
+//                8 builder warps load the fp32 state rows (coalesced, one stage ahead), split them into fp16 hi/lo and
+//                store them straight into swizzled shared memory; the issuer thread streams the pre-swizzled hi/lo
+//                weight image with cp.async.bulk (UBLKCP) into a ring and issues tcgen05.mma kind::f16 (M = 128,
+//                N = 64..256, fp16 x 3 split, fp32 accumulators in TMEM); the builder warps drain TMEM into P / Gi rows.
+// States written in one phase are read in later phases by OTHER CTAs: all such reads use ld.global.cg (L2), the
 // barrier is the cooperative-groups pattern (bar.sync; fence; atomic; spin on ld.acquire; bar.sync).
 #include "common.cuh"
 #include "tc.cuh"
@@ -28,18 +27,17 @@
 namespace dagnn {
 
 constexpr int kBuilderWarps = 8;
-constexpr int kBuilders = kBuilderWarps * 32;            // 256 threads build operands and run the epilogue
+constexpr int kBuilders = kBuilderWarps * 32;            // 256 threads: gate phase, operand build, epilogue
+constexpr int kThreads = kBuilders + 32;                 // + one warp whose lane 0 issues bulk copies and MMAs
 constexpr int kNR = 128 * 8 / kBuilders;                 // rows of a 128-row operand stage per builder thread
 constexpr int kRStride = 128 / kNR;
-constexpr int kThreads = kBuilders + 32;                 // + one warp whose lane 0 issues bulk copies and MMAs
 constexpr int kAStageBytes = 2 * 128 * tc::ROW_BYTES;    // hi + lo tile of 128 rows x 64 k  = 32 KB
 constexpr int kNAS = 2;                                  // operand stages
-constexpr int kBRegionBytes = 2 * 2 * 192 * tc::ROW_BYTES;   // weight ring: 2 stages of 48 KB (U = 64) or 8 of 12 KB (U = 16)
+constexpr int kBlkBytes = 2 * 64 * tc::ROW_BYTES;        // hi + lo tile of one 64-column block x 64 k = 16 KB
+constexpr int kBRegionBytes = 8 * kBlkBytes;             // weight ring: 2 x 4 blocks, 4 x 2 blocks or 8 x 1 block = 128 KB
 constexpr int kNBBar = 8;
-constexpr int kEdgeCap = 3072;                           // in-edges of one tile cached in shared memory (else: global scratch)
-constexpr int kMaxRows = 256;                            // rows per tile (two 128-row sub-tiles share every weight chunk)
 constexpr int kMaxSeg = DAGNN_MAX_DIRS * DAGNN_MAX_LAYERS;
-constexpr int kTmemCols = 512;                           // 2 sub-tiles x [n_in | r | z | n_hid] x 64 units
+constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 columns
 constexpr int kMaxSmem = 232448;                         // 227 KB opt-in limit per CTA on sm_100
 
 struct DirP {
@@ -50,29 +48,26 @@ struct DirP {
   const int* lvl_off;   // [max_levels+1] first position of each level
 };
 struct LayP {
-  float* Hs;            // H[d][i], [N, ldh] position order: predecessor rows read, this level's rows written
+  float* Hs;            // H[d][i], [N, ldh] position order
+  float* sk;            // [N] key score wk . h of every node
+  float* Pm;            // [N, Mc] W_hh^i h^i_j  (columns gate * Hq + unit)
+  float* Gi;            // [N, Mc] W_ih^i inp_v
   const float* bias;    // [4][HP]
   const float* wk;      // [HP]
   const float* attnc;   // [4]
   const float* vidk;    // [nvid]
-  const __half* img16;  // weight images (pack.cu)
-  const __half* img64;
-  float* alpha;         // [E] scratch: softmax weights of tiles whose edge list exceeds the shared-memory cache
-  float* skp;           // [N][nskp] partial key scores wk . h over 16-unit groups, written with every state row
+  const __half* imgh;   // [W_hh^i ; W_ih^{i+1}] image (pack.cu)
+  const __half* imgx;   // W_ih^0 image (layer 0 only)
 };
-constexpr int kHeavy = 2;                                // rows with more in-edges get their aggregate precomputed per tile
-constexpr int kVeryHeavy = 24;                           // ... by the whole CTA instead of one warp
-constexpr int kMaxVH = 16;
 struct SweepP {
-  int dirs, layers, H, Hq, nvid, use_ea;
-  int Din0, nci0, ncih;       // layer-0 input width, 64-k chunks of the layer-0 input / of a hidden-width operand
-  int NG, NT, nskp, vec_x;    // 16-unit groups, 64-unit tiles, row stride of skp, X rows are float4-loadable
+  int dirs, layers, H, Hq, Mc, HP, nvid, use_ea;
+  int Din0, nckx, nckh;       // layer-0 input width, 64-k chunks of the layer-0 input / of a state operand
+  int vec_x, N;
   long long ldh, ldx;
   const float* X;             // [N, ldx] node order (rows through perm)
   const int* summary;         // [0] number of levels of direction 0, [2] schedule status
   unsigned int* bar;          // grid barrier counter (zeroed by the launcher)
-  float* heavy;               // [grid][kMaxRows][Hq] per-CTA scratch: aggregates m_v of the tile's high-in-degree rows
-  long long* trace;           // optional [steps][256][16] clock64 stamps, nullptr = off
+  long long* trace;           // optional [steps + 1][256][16] clock64 stamps, nullptr = off
   DirP dir[DAGNN_MAX_DIRS];
   LayP lay[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
 };
@@ -82,17 +77,10 @@ struct Seg {
 };
 struct StepTab {
   Seg seg[kMaxSeg];
-  int U, nst;                 // units per tile, 128-row sub-tiles per tile
+  int nbc, nst;               // 64-column blocks per tile (1, 2, 4), 128-row sub-tiles per tile
 };
 struct SmemTail {
-  float alpha[kEdgeCap];
-  int col[kEdgeCap];
-  int rp[kMaxRows + 4];
-  int nidx[kMaxRows];
-  StepTab tab[2];             // this step's and the next step's segment tables
-  float bias[5][64];          // b_r, b_z, b_in, b_hn, wk of the tile's units
-  int vh[kMaxVH];             // rows of the tile whose edge list the whole CTA aggregates
-  int nvh;
+  StepTab tab[2];             // this proj phase's and the next one's segment tables
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
   uint32_t tmem_slot;
 };
@@ -125,7 +113,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory"); }
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -143,284 +130,177 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   __syncthreads();
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-struct Tile {                 // one work item, identical in every thread of the CTA
-  int d, i, level0, pos0, p0, nrows, nst, ut, nci, nchunks;
-};
-
-// ------------------------------------------------------------------------------------------------------------
-// builders: softmax weights, operand tiles, epilogue
-// ------------------------------------------------------------------------------------------------------------
-// position of hidden chunk h in the processing order: the chunk that holds the tile's own units goes LAST, so that its
-// operand stage (m_v of exactly these units, as hi + lo) is still in shared memory when the epilogue needs h_prev
-__device__ __forceinline__ int hperm(int h, int nch, int own) { return h == nch - 1 ? own : (h < own ? h : h + 1); }
-
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
+  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
+}
 
-// raw operands of one work item of a builder thread, loaded one item ahead: kNR rows (r0 + x * kRStride of the sub-tile),
-// up to two weighted source rows each (the input row with weight 1, or the first two in-edges), 8 consecutive k
-struct Pre {
-  float4 v[kNR][2][2];    // [row][source][half]
-  float w[kNR][2];
+// ------------------------------------------------------------------------------------------------------------
+// gate phase: one warp per node. Lane l owns the units 4 l + 128 j (+ 0..3), j < J, of a 128 J wide column pass.
+// ------------------------------------------------------------------------------------------------------------
+template <int J>
+__device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, bool level0, int lane) {
+  const int Hq = P.Hq, Mc = P.Mc, HP = P.HP;
+  const long long ldh = P.ldh;
+  const float* __restrict__ gi = Lp.Gi + (size_t)p * Mc;
+  const float* __restrict__ Pm = Lp.Pm;
+  const float* __restrict__ Hs = Lp.Hs;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e0 = 0, e1 = 0;
+  float mx = 0.f, inv = 0.f;
+  const bool use_ea = P.use_ea && D.eattr != nullptr;
+  const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
+  // score of in-edge e (lane-private): key score of the predecessor if it sits in an earlier level, else 0 — such an edge
+  // keeps its softmax mass and adds a zero row — plus the edge-type / vertex-id terms
+  auto score = [&](int e, int& sp) {
+    sp = D.col[e];
+    float sc = (sp < pos0) ? __ldcg(Lp.sk + sp) : 0.f;
+    if (use_ea) {
+      const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
+      sc += ca0 * ea.x + ca1 * ea.y;
+    }
+    if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
+    return sc;
+  };
+  if (!level0) {
+    e0 = D.rowptr[p];
+    e1 = D.rowptr[p + 1];
+    float sum = 0.f;
+    mx = -INFINITY;
+    for (int eb = e0; eb < e1; eb += 32) {                 // softmax statistics, 32 in-edges per round
+      const int e = eb + lane;
+      int sp;
+      const float sc = (e < e1) ? score(e, sp) : -INFINITY;
+      const float mnew = fmaxf(mx, warp_max(sc));
+      sum = sum * expf(mx - mnew) + warp_sum((e < e1) ? expf(sc - mnew) : 0.f);
+      mx = mnew;
+    }
+    inv = (e1 > e0) ? 1.f / (sum + 1e-16f) : 0.f;
+  }
+  float skacc = 0.f;
+#pragma unroll 1
+  for (int ub = 0; ub < Hq; ub += 128 * J) {
+    float4 ar[J], az[J], an[J], am[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { ar[j] = z4; az[j] = z4; an[j] = z4; am[j] = z4; }
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int e = eb + lane;
+      int my_sp = 0;
+      float my_a = 0.f;
+      if (e < e1) {
+        const float sc = score(e, my_sp);
+        my_a = (my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
+      }
+      const int ne = min(32, e1 - eb);
+      for (int q = 0; q < ne; ++q) {
+        const float a = __shfl_sync(0xffffffffu, my_a, q);
+        const int sp = __shfl_sync(0xffffffffu, my_sp, q);
+        if (a == 0.f) continue;                            // warp-uniform
+        const float* pr = Pm + (size_t)sp * Mc;
+        const float* hr = Hs + (size_t)sp * ldh;
+        float4 vr[J], vz[J], vn[J], vh[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int u = ub + 4 * lane + 128 * j;
+          vr[j] = z4; vz[j] = z4; vn[j] = z4; vh[j] = z4;
+          if (u < Hq) {
+            vr[j] = ldcg4(pr + u);
+            vz[j] = ldcg4(pr + Hq + u);
+            vn[j] = ldcg4(pr + 2 * Hq + u);
+            vh[j] = ldcg4(hr + u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) { fma4(ar[j], a, vr[j]); fma4(az[j], a, vz[j]); fma4(an[j], a, vn[j]); fma4(am[j], a, vh[j]); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int u = ub + 4 * lane + 128 * j;
+      if (u >= Hq) continue;
+      const float4 gr = ldcg4(gi + u), gz = ldcg4(gi + Hq + u), gn = ldcg4(gi + 2 * Hq + u);
+      const float4 br = __ldg(reinterpret_cast<const float4*>(Lp.bias + u));
+      const float4 bz = __ldg(reinterpret_cast<const float4*>(Lp.bias + HP + u));
+      const float4 bi = __ldg(reinterpret_cast<const float4*>(Lp.bias + 2 * HP + u));
+      const float4 bh = __ldg(reinterpret_cast<const float4*>(Lp.bias + 3 * HP + u));
+      const float4 wk = __ldg(reinterpret_cast<const float4*>(Lp.wk + u));
+      float4 o;
+#define DAGNN_GATE(c)                                                          \
+  {                                                                            \
+    const float rg = fast_sigmoid(gr.c + ar[j].c + br.c);                      \
+    const float zg = fast_sigmoid(gz.c + az[j].c + bz.c);                      \
+    const float ng = fast_tanh(gn.c + bi.c + rg * (an[j].c + bh.c));           \
+    o.c = ng + zg * (am[j].c - ng);                                            \
+  }
+      DAGNN_GATE(x) DAGNN_GATE(y) DAGNN_GATE(z) DAGNN_GATE(w)
+#undef DAGNN_GATE
+      *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * ldh + u) = o;
+      skacc += o.x * wk.x + o.y * wk.y + o.z * wk.z + o.w * wk.w;       // units >= H: zero weights and biases -> o = 0
+    }
+  }
+  skacc = warp_sum(skacc);
+  if (lane == 0) Lp.sk[p] = skacc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// proj phase
+// ------------------------------------------------------------------------------------------------------------
+struct Tile {                 // one projection work item, identical in every thread of the CTA
+  const float* A;             // operand rows (fp32): states in position order, or X through perm
+  long long lda;
+  const int* perm;            // non-null: operand row of position p is A[perm[p]]
+  const __half* img;          // weight image of the source
+  float* out0;                // columns [0, Mc)
+  float* out1;                // columns [Mc, 2 Mc) or nullptr
+  int K, nck, vec;            // valid operand width, 64-k chunks, rows are float4-loadable
+  int p0, nrows, nst, cb0, ncb;   // first position, rows, 128-row sub-tiles, first 64-column block, blocks in this tile
 };
 
-__device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int U, unsigned char* As, SmemTail& S, uint32_t tmem,
-                                             uint32_t ja, uint32_t ct, long long* tr) {
+// raw operands of one work item of a builder thread, loaded one item ahead: kNR rows (r0 + x * kRStride of the sub-tile),
+// 8 consecutive k
+struct Pre {
+  float4 v[kNR][2];
+};
+
+__device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory"); }
+
+__device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, unsigned char* As, SmemTail& S, uint32_t tmem, uint32_t ja,
+                                             uint32_t ct, int tile_cols, long long* tr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const DirP& D = P.dir[T.d];
-  const LayP& Lp = P.lay[T.d][T.i];
-  const float* __restrict__ Hcur = Lp.Hs;
-  const long long ldh = P.ldh;
-  const int Hq = P.Hq;
-  const bool level0 = T.level0 != 0;
   const bool trc = tr != nullptr && tid == 0;
-#ifdef DAGNN_TRACE_FINE
-  long long t_pre = 0, t_wait = 0, t_build = 0, t_hand = 0, t_comb = 0, t_pref = 0, t0 = 0;
-  if (trc) t0 = clock64();
-#define TRC_ACC(var) if (trc) { const long long t1 = clock64(); var += t1 - t0; t0 = t1; }
-#else
-#define TRC_ACC(var)
-#endif
-
-  builders_sync();            // previous tile: epilogue reads of rp / alpha / col / bias are done
-  for (int t = tid; t <= T.nrows; t += kBuilders) S.rp[t] = level0 ? 0 : D.rowptr[T.p0 + t];
-  for (int t = tid; t < T.nrows; t += kBuilders) S.nidx[t] = (T.i == 0) ? D.perm[T.p0 + t] : T.p0 + t;
-  {
-    const int HP = P.NT * 64, ub = T.ut * U;
-    for (int t = tid; t < 5 * U; t += kBuilders) {
-      const int g = t / U, u = ub + (t - g * U);
-      S.bias[g][t - g * U] = (g < 4) ? __ldg(Lp.bias + g * HP + u) : __ldg(Lp.wk + u);
-    }
-  }
-  builders_sync();
-  const int ebase = S.rp[0];
-  const int ecount = S.rp[T.nrows] - ebase;
-  const bool fits = ecount <= kEdgeCap;
-
-  // ---------------- pre-phase: softmax weights of every in-edge of the tile's rows ----------------
-  if (!level0) {
-    const bool use_ea = P.use_ea && D.eattr != nullptr;
-    const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
-    auto score = [&](int e, int& sp) {
-      sp = D.col[e];
-      float sc = 0.f;
-      if (sp < T.pos0) {                               // predecessor state exists (earlier level), else a zero row
-        const float* kp = Lp.skp + (size_t)sp * P.nskp;
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int j = 0;
-        for (; j + 4 <= P.NG; j += 4) {
-          const float4 v = ldcg4(kp + j);
-          a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
-        }
-        for (; j < P.NG; ++j) a4.x += __ldcg(kp + j);
-        sc = (a4.x + a4.y) + (a4.z + a4.w);
-      }
-      if (use_ea) {
-        const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
-        sc += ca0 * ea.x + ca1 * ea.y;
-      }
-      if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
-      return sc;
-    };
-    if (fits) {
-      // edge-parallel scores (one dependent chain col -> key-score partials for the whole tile), then a per-row softmax
-      // over shared memory. A not-yet-computed predecessor keeps its softmax mass and adds a zero row.
-      for (int idx = tid; idx < ecount; idx += kBuilders) {
-        int sp;
-        S.alpha[idx] = score(ebase + idx, sp);
-        S.col[idx] = sp;
-      }
-      builders_sync();
-      if (tid < T.nrows) {
-        const int i0 = S.rp[tid] - ebase, i1 = S.rp[tid + 1] - ebase;
-        float mx = -INFINITY, sum = 0.f;
-        for (int k = i0; k < i1; ++k) mx = fmaxf(mx, S.alpha[k]);
-        for (int k = i0; k < i1; ++k) sum += expf(S.alpha[k] - mx);
-        const float inv = 1.f / (sum + 1e-16f);
-        for (int k = i0; k < i1; ++k) S.alpha[k] = (S.col[k] < T.pos0) ? expf(S.alpha[k] - mx) * inv : 0.f;
-      }
-      // rows with many in-edges: their aggregate m_v = sum_e alpha_e h_e is computed once per tile over the full width
-      // and parked in this CTA's scratch; the row then looks like a single in-edge of weight 1 to the operand builders
-      // (whose per-item gather is serial over edges). Up to kVeryHeavy in-edges: one warp per row, four predecessor
-      // rows x 256 columns in flight; beyond: the whole CTA splits the edge list of the row, partials meet in shared
-      // memory (the operand stages are idle during the pre-phase).
-      if (tid == 0) S.nvh = 0;
-      builders_sync();
-      float* scr = P.heavy + (size_t)blockIdx.x * kMaxRows * Hq;
-      auto agg_edges = [&](int kb, int k0, int k1, int kstep, float4& acc0, float4& acc1) {
-        const bool two = kb + 128 < Hq;
-        for (int k = k0; k < k1; k += 4 * kstep) {
-          float w[4];
-          float4 h0[4], h1[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int kk = k + t * kstep;
-            w[t] = (kk < k1) ? S.alpha[kk] : 0.f;
-            h0[t] = make_float4(0.f, 0.f, 0.f, 0.f); h1[t] = h0[t];
-            if (w[t] != 0.f) {
-              const float* hr = Hcur + (size_t)S.col[kk] * ldh + kb;
-              h0[t] = ldcg4(hr);
-              if (two) h1[t] = ldcg4(hr + 128);
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            acc0.x = fmaf(w[t], h0[t].x, acc0.x); acc0.y = fmaf(w[t], h0[t].y, acc0.y);
-            acc0.z = fmaf(w[t], h0[t].z, acc0.z); acc0.w = fmaf(w[t], h0[t].w, acc0.w);
-            acc1.x = fmaf(w[t], h1[t].x, acc1.x); acc1.y = fmaf(w[t], h1[t].y, acc1.y);
-            acc1.z = fmaf(w[t], h1[t].z, acc1.z); acc1.w = fmaf(w[t], h1[t].w, acc1.w);
-          }
-        }
-      };
-      auto mark_row = [&](int r, int i0, int i1, int first_lane_k) {       // one warp: row r now reads scratch row r
-        for (int k = i0 + first_lane_k; k < i1; k += 32) {
-          S.alpha[k] = (k == i0) ? 1.f : 0.f;
-          if (k == i0) S.col[k] = ~r;                    // negative: row r of the scratch
-        }
-      };
-      const bool vh_ok = (size_t)kBuilderWarps * Hq * sizeof(float) <= (size_t)kNAS * kAStageBytes;
-      for (int r = warp; r < T.nrows; r += kBuilderWarps) {
-        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
-        if (i1 - i0 <= kHeavy) continue;                 // warp-uniform
-        if (vh_ok && i1 - i0 > kVeryHeavy) {
-          int slot = 0;
-          if (lane == 0) slot = atomicAdd(&S.nvh, 1);
-          slot = __shfl_sync(0xffffffffu, slot, 0);
-          if (slot < kMaxVH) {
-            if (lane == 0) S.vh[slot] = r;
-            continue;
-          }
-        }
-        for (int kb = 4 * lane; kb < Hq; kb += 256) {
-          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-          agg_edges(kb, i0, i1, 1, acc0, acc1);
-          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = acc0;
-          if (kb + 128 < Hq) *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb + 128) = acc1;
-        }
-        __syncwarp();
-        mark_row(r, i0, i1, lane);
-      }
-      builders_sync();
-      const int nvh = min(S.nvh, kMaxVH);
-      float* part = reinterpret_cast<float*>(As);        // [kBuilderWarps][Hq] partial aggregates
-      for (int v = 0; v < nvh; ++v) {
-        const int r = S.vh[v];
-        const int i0 = S.rp[r] - ebase, i1 = S.rp[r + 1] - ebase;
-        for (int kb = 4 * lane; kb < Hq; kb += 256) {
-          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-          agg_edges(kb, i0 + warp, i1, kBuilderWarps, acc0, acc1);
-          *reinterpret_cast<float4*>(part + (size_t)warp * Hq + kb) = acc0;
-          if (kb + 128 < Hq) *reinterpret_cast<float4*>(part + (size_t)warp * Hq + kb + 128) = acc1;
-        }
-        builders_sync();
-        for (int kb = 4 * tid; kb < Hq; kb += 4 * kBuilders) {
-          float4 a = *reinterpret_cast<const float4*>(part + kb);
-#pragma unroll
-          for (int w = 1; w < kBuilderWarps; ++w) {
-            const float4 b = *reinterpret_cast<const float4*>(part + (size_t)w * Hq + kb);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          *reinterpret_cast<float4*>(scr + (size_t)r * Hq + kb) = a;
-        }
-        if (warp == 0) mark_row(r, i0, i1, lane);
-        builders_sync();
-      }
-    } else if (tid < T.nrows) {
-      // edge list larger than the cache: row-serial, softmax weights in global scratch. Only FINAL weights are stored —
-      // the CTAs of the other unit tiles of these rows write the same values to the same addresses concurrently.
-      const int e0 = S.rp[tid], e1 = S.rp[tid + 1];
-      float mx = -INFINITY, sum = 0.f;
-      int sp;
-      for (int e = e0; e < e1; ++e) {
-        const float sc = score(e, sp);
-        const float mnew = fmaxf(mx, sc);
-        sum = sum * expf(mx - mnew) + expf(sc - mnew);
-        mx = mnew;
-      }
-      const float inv = 1.f / (sum + 1e-16f);
-      for (int e = e0; e < e1; ++e) {
-        const float sc = score(e, sp);
-        Lp.alpha[e] = (sp < T.pos0) ? expf(sc - mx) * inv : 0.f;
-      }
-    }
-    builders_sync();
-  }
-  const float* __restrict__ ga = Lp.alpha;
-  const int* __restrict__ gc = D.col;
-  auto alpha_of = [&](int e) { return fits ? S.alpha[e - ebase] : __ldcg(ga + e); };
-  auto col_of = [&](int e) { return fits ? S.col[e - ebase] : gc[e]; };
-  TRC_ACC(t_pre)
-
-  // ---------------- main loop: operand tiles, raw loads one item ahead ----------------
   const int r0 = tid >> 3, c8 = tid & 7;
-  const float* inp = (T.i == 0) ? P.X : P.lay[T.d][T.i - 1].Hs;
-  const long long ld_inp = (T.i == 0) ? P.ldx : P.ldh;
-  const int Din = (T.i == 0) ? P.Din0 : Hq;              // layers > 0: rows are zero-padded to Hq
-  const bool vec_in = (T.i > 0) || P.vec_x;
-  const int nch = T.nchunks - T.nci;
-  const int own = (T.ut * U) >> 6;                       // hidden chunk that covers the tile's own units
-  const int nitems = T.nchunks * T.nst;
+  const int nitems = T.nck * T.nst;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* scr_ = P.heavy + (size_t)blockIdx.x * kMaxRows * Hq;
-
   // row groups (of kRStride rows) a sub-tile really has: the tail levels hold a handful of rows per tile
   auto groups_of = [&](int st) { return min(kNR, (min(128, T.nrows - st * 128) + kRStride - 1) / kRStride); };
   auto prefetch = [&](int it, Pre& R) {
     if (it >= nitems) return;
     const int c = it / T.nst, st = it - c * T.nst;
     const int nx = groups_of(st);
+    const int k0 = c * tc::KC16 + 8 * c8;
 #pragma unroll
-    for (int x = 0; x < kNR; ++x)
-      if (x < nx) {
+    for (int x = 0; x < kNR; ++x) {
+      if (x >= nx) continue;
+      R.v[x][0] = z4; R.v[x][1] = z4;
+      const int r = st * 128 + r0 + kRStride * x;
+      if (r >= T.nrows || k0 >= T.K) continue;
+      const int p = T.p0 + r;
+      const float* src = T.A + (size_t)(T.perm ? T.perm[p] : p) * T.lda + k0;
+      if (T.vec) {
+        R.v[x][0] = ldcg4(src);
+        if (k0 + 4 < T.K) R.v[x][1] = ldcg4(src + 4);
+      } else {
+        float t[8];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) { R.v[x][k][0] = z4; R.v[x][k][1] = z4; R.w[x][k] = 0.f; }
-      }
-    const int ra = st * 128 + r0;
-    if (c < T.nci) {
-      const int k0 = c * tc::KC16 + 8 * c8;
-      if (k0 >= Din) return;
-      const bool two = k0 + 4 < Din;
-#pragma unroll
-      for (int x = 0; x < kNR; ++x) {
-        const int r = ra + kRStride * x;
-        if (x >= nx || r >= T.nrows) continue;
-        const float* src = inp + (size_t)S.nidx[r] * ld_inp + k0;
-        R.w[x][0] = 1.f;
-        if (vec_in) {
-          R.v[x][0][0] = ldcg4(src);
-          if (two) R.v[x][0][1] = ldcg4(src + 4);
-        } else {
-          float t[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) t[q] = (k0 + q < Din) ? __ldcg(src + q) : 0.f;
-          R.v[x][0][0] = make_float4(t[0], t[1], t[2], t[3]);
-          R.v[x][0][1] = make_float4(t[4], t[5], t[6], t[7]);
-        }
-      }
-    } else {
-      const int k0 = hperm(c - T.nci, nch, own) * tc::KC16 + 8 * c8;
-      if (k0 >= Hq) return;
-      const bool two = k0 + 4 < Hq;
-#pragma unroll
-      for (int x = 0; x < kNR; ++x) {
-        const int r = ra + kRStride * x;
-        if (x >= nx || r >= T.nrows) continue;
-        const int e0 = S.rp[r], e1 = S.rp[r + 1];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (e0 + k < e1) {
-            const float w = alpha_of(e0 + k);
-            R.w[x][k] = w;
-            if (w != 0.f) {
-              const int cc = col_of(e0 + k);
-              const float* hr = (cc >= 0 ? Hcur + (size_t)cc * ldh : scr_ + (size_t)(~cc) * Hq) + k0;
-              R.v[x][k][0] = ldcg4(hr);
-              if (two) R.v[x][k][1] = ldcg4(hr + 4);
-            }
-          }
-        }
+        for (int q = 0; q < 8; ++q) t[q] = (k0 + q < T.K) ? __ldcg(src + q) : 0.f;
+        R.v[x][0] = make_float4(t[0], t[1], t[2], t[3]);
+        R.v[x][1] = make_float4(t[4], t[5], t[6], t[7]);
       }
     }
   };
@@ -429,143 +309,56 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
   prefetch(0, R);
 #pragma unroll 1
   for (int it = 0; it < nitems; ++it) {
-    const int c = it / T.nst, st = it - c * T.nst;
+    const int st = it % T.nst;
     const uint32_t j = ja + (uint32_t)it;
     const uint32_t stage = j % kNAS, use = j / kNAS;
     unsigned char* A_hi = As + (size_t)stage * kAStageBytes;
     unsigned char* A_lo = A_hi + 128 * tc::ROW_BYTES;
-    // combine the prefetched sources, then put the next item's loads in flight before anything else
-    float x[kNR][8];
     const int nx = groups_of(st);
+    float x[kNR][8];
 #pragma unroll
     for (int q = 0; q < kNR; ++q) {
       if (q >= nx) continue;
-      const float w0 = R.w[q][0], w1 = R.w[q][1];
-      const float4 a0 = R.v[q][0][0], a1 = R.v[q][0][1], b0 = R.v[q][1][0], b1 = R.v[q][1][1];
-      x[q][0] = fmaf(w1, b0.x, w0 * a0.x); x[q][1] = fmaf(w1, b0.y, w0 * a0.y); x[q][2] = fmaf(w1, b0.z, w0 * a0.z); x[q][3] = fmaf(w1, b0.w, w0 * a0.w);
-      x[q][4] = fmaf(w1, b1.x, w0 * a1.x); x[q][5] = fmaf(w1, b1.y, w0 * a1.y); x[q][6] = fmaf(w1, b1.z, w0 * a1.z); x[q][7] = fmaf(w1, b1.w, w0 * a1.w);
+      const float4 a0 = R.v[q][0], a1 = R.v[q][1];
+      x[q][0] = a0.x; x[q][1] = a0.y; x[q][2] = a0.z; x[q][3] = a0.w; x[q][4] = a1.x; x[q][5] = a1.y; x[q][6] = a1.z; x[q][7] = a1.w;
     }
-    TRC_ACC(t_comb)
-    prefetch(it + 1, R);
-    TRC_ACC(t_pref)
+    prefetch(it + 1, R);                                               // next item's loads in flight before anything else
+    if (use >= 1) mbar_wait(&S.a_empty[stage], (use - 1) & 1u);        // MMAs that read this stage are done
     const int ra = st * 128 + r0;
-    if (c >= T.nci) {                                    // rows with more than two in-edges: the rest, two edges in flight
-      const int k0 = hperm(c - T.nci, nch, own) * tc::KC16 + 8 * c8;
-      if (k0 < Hq) {
-        const bool two = k0 + 4 < Hq;
 #pragma unroll
-        for (int q = 0; q < kNR; ++q) {
-          const int r = ra + kRStride * q;
-          if (q >= nx || r >= T.nrows) continue;
-          const int e1 = S.rp[r + 1];
-          for (int e = S.rp[r] + 2; e < e1; e += 2) {
-            float w[2];
-            float4 h0[2], h1[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              w[k] = (e + k < e1) ? alpha_of(e + k) : 0.f;
-              h0[k] = z4; h1[k] = z4;
-              if (w[k] != 0.f) {
-                const float* hr = Hcur + (size_t)col_of(e + k) * ldh + k0;
-                h0[k] = ldcg4(hr);
-                if (two) h1[k] = ldcg4(hr + 4);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              x[q][0] = fmaf(w[k], h0[k].x, x[q][0]); x[q][1] = fmaf(w[k], h0[k].y, x[q][1]); x[q][2] = fmaf(w[k], h0[k].z, x[q][2]); x[q][3] = fmaf(w[k], h0[k].w, x[q][3]);
-              x[q][4] = fmaf(w[k], h1[k].x, x[q][4]); x[q][5] = fmaf(w[k], h1[k].y, x[q][5]); x[q][6] = fmaf(w[k], h1[k].z, x[q][6]); x[q][7] = fmaf(w[k], h1[k].w, x[q][7]);
-            }
-          }
-        }
-      }
-    }
-    TRC_ACC(t_build)
-    if (use >= 1) mbar_wait(&S.a_empty[stage], (use - 1) & 1u);     // MMAs that read this stage are done
-    TRC_ACC(t_wait)
-#pragma unroll
-    for (int q = 0; q < kNR; ++q)                                           // rows beyond the tile: D rows nobody reads
+    for (int q = 0; q < kNR; ++q)                                      // rows beyond the tile: D rows nobody reads
       if (q < nx && ra + kRStride * q < T.nrows) tc::store_split8(A_hi, A_lo, r0 + kRStride * q, c8, x[q]);
-    TRC_ACC(t_build)
     tc::fence_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.a_full[stage]);
-    TRC_ACC(t_hand)
   }
   if (trc) tr[1] = clock64();
-#ifdef DAGNN_TRACE_FINE
-  if (trc) { tr[8] = t_pre; tr[9] = t_wait; tr[10] = t_build; tr[11] = t_hand; tr[12] = t_comb; tr[13] = t_pref; }
-#endif
 
-  // ---------------- epilogue ----------------
+  // ---------------- epilogue: TMEM -> P / Gi rows ----------------
   mbar_wait(&S.acc_full, ct & 1u);
   tc::fence_after_sync();
   if (trc) tr[2] = clock64();
   {
     const int q = warp & 3, cg = warp >> 2;
-    const int ng16 = U >> 4;
-    const int ucol0 = (T.ut * U) & 63;                   // first own unit inside its 64-k chunk
+    const int ngrp = T.ncb * 8;                           // 8-column groups of the tile
+    const int Mc = P.Mc;
 #pragma unroll 1
     for (int st = 0; st < T.nst; ++st) {
-      const int rr = 32 * q + lane;                      // row inside the sub-tile = TMEM lane
-      const int r = st * 128 + rr;
+      const int r = st * 128 + 32 * q + lane;            // TMEM lane = row inside the sub-tile
       const bool rok = r < T.nrows;
-      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(st * 4 * U);
-      // the sub-tile's last operand stage still holds m_v of the own units (hi + lo)
-      const uint32_t jl = ja + (uint32_t)((T.nchunks - 1) * T.nst + st);
-      const unsigned char* H_hi = As + (size_t)(jl % kNAS) * kAStageBytes;
-      const unsigned char* H_lo = H_hi + 128 * tc::ROW_BYTES;
+      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(st * tile_cols);
 #pragma unroll 1
-      for (int g16 = cg; g16 < ng16; g16 += kBuilderWarps / 4) {
-        const int u0 = T.ut * U + g16 * 16;
-        if (u0 >= Hq) break;                              // warp-uniform
-        float pk = 0.f;
-#pragma unroll 1
-        for (int h8 = 0; h8 < 2; ++h8) {
-          const int cu = g16 * 16 + 8 * h8;               // column inside the tile's unit range
-          const int uu = u0 + 8 * h8;
-          if (uu >= Hq) break;                            // warp-uniform
-          float an[8], ar[8], az[8], ah_[8];
-          __syncwarp();
-          tc::ld8(tbase + (uint32_t)cu, an);
-          tc::ld8(tbase + (uint32_t)(U + cu), ar);
-          tc::ld8(tbase + (uint32_t)(2 * U + cu), az);
-          if (!level0) tc::ld8(tbase + (uint32_t)(3 * U + cu), ah_);
-          float hp[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) hp[t] = 0.f;
-          if (!level0) {
-            const uint32_t off = tc::tile_off(rr, (ucol0 + cu) >> 3);
-            const uint4 hh = *reinterpret_cast<const uint4*>(H_hi + off);
-            const uint4 hl = *reinterpret_cast<const uint4*>(H_lo + off);
-            const uint32_t* ph = reinterpret_cast<const uint32_t*>(&hh);
-            const uint32_t* pl = reinterpret_cast<const uint32_t*>(&hl);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ph[t]));
-              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&pl[t]));
-              hp[2 * t] = fh.x + fl.x;
-              hp[2 * t + 1] = fh.y + fl.y;
-            }
-          }
-          tc::wait_ld();
-          float o[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int ul = cu + t;
-            const float rg = fast_sigmoid(ar[t] + S.bias[0][ul]);
-            const float zg = fast_sigmoid(az[t] + S.bias[1][ul]);
-            const float ng = fast_tanh(an[t] + S.bias[2][ul] + rg * ((level0 ? 0.f : ah_[t]) + S.bias[3][ul]));
-            o[t] = ng + zg * (hp[t] - ng);
-            pk = fmaf(o[t], S.bias[4][ul], pk);
-          }
-          if (rok) {
-            float* dst = Lp.Hs + (size_t)(T.p0 + r) * ldh + uu;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            if (uu + 4 < Hq) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
+      for (int g = cg; g < ngrp; g += kBuilderWarps / 4) {
+        float v[8];
+        __syncwarp();
+        tc::ld8(tbase + (uint32_t)(8 * g), v);
+        tc::wait_ld();
+        if (rok) {
+          const int col = T.cb0 * 64 + 8 * g;
+          float* dst = (col < Mc) ? T.out0 + (size_t)(T.p0 + r) * Mc + col : T.out1 + (size_t)(T.p0 + r) * Mc + (col - Mc);
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
-        if (rok) Lp.skp[(size_t)(T.p0 + r) * P.nskp + (u0 >> 4)] = pk;
       }
     }
     tc::fence_before_sync();
@@ -575,46 +368,17 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, int
 
 // ------------------------------------------------------------------------------------------------------------
 // issuer (one thread): weight ring + MMA issue. Ring barriers are tracked per physical barrier (the ring geometry
-// changes with U between steps; at a step boundary every stage is drained).
+// changes with the tile width between phases).
 // ------------------------------------------------------------------------------------------------------------
 struct RingState {
   uint32_t full_par, empty_par, pending;     // bit s: parity of the next wait on b_full[s] / b_empty[s]; commit outstanding
   uint32_t next;                             // next stage to fill
   uint32_t pre, pre_first;                   // chunks of the upcoming tile already in flight, stage of its chunk 0
-  int U;                                     // units per tile the ring is currently laid out for (2 x 48 KB or 8 x 12 KB stages)
+  int nbc;                                   // blocks per stage the ring is currently laid out for (8 / nbc stages)
 };
-struct BSrc {                                // where the weight chunks of a tile come from, and the ring geometry for its U
-  const unsigned char* img;
-  uint32_t bstage;
-  int nbs, nci, nch, own;
-};
-__device__ __forceinline__ BSrc make_bsrc(const SweepP& P, const Tile& T, int U) {
-  const LayP& Lp = P.lay[T.d][T.i];
-  BSrc b;
-  b.nbs = (U == 64) ? 2 : 8;
-  b.bstage = 2u * 3u * (uint32_t)U * tc::ROW_BYTES;                         // hi + lo tile of 3U rows
-  const int nc_all = ((T.i == 0) ? P.nci0 : P.ncih) + P.ncih;               // chunks per unit block in the image
-  b.img = reinterpret_cast<const unsigned char*>(U == 64 ? Lp.img64 : Lp.img16) + (size_t)T.ut * nc_all * b.bstage;
-  b.nci = T.nci; b.nch = T.nchunks - T.nci; b.own = (T.ut * U) >> 6;
-  return b;
-}
-// weight chunk at processing position c of a tile -> next ring stage
-__device__ __forceinline__ void ring_load(const BSrc& b, int c, unsigned char* Bs, SmemTail& S, RingState& R) {
-  if (c >= b.nci) c = b.nci + hperm(c - b.nci, b.nch, b.own);
-  const uint32_t s = R.next;
-  R.next = (s + 1 == (uint32_t)b.nbs) ? 0u : s + 1;
-  if (R.pending >> s & 1u) {                         // MMAs that read this stage must be done
-    mbar_wait(&S.b_empty[s], R.empty_par >> s & 1u);
-    R.empty_par ^= 1u << s;
-    R.pending &= ~(1u << s);
-  }
-  mbar_expect_tx(&S.b_full[s], b.bstage);
-  bulk_g2s(Bs + (size_t)s * b.bstage, b.img + (size_t)c * b.bstage, b.bstage, &S.b_full[s]);
-}
-
-// the ring geometry changes with U: every stage must be drained before the region is re-cut
-__device__ __forceinline__ void ring_set_geometry(int U, SmemTail& S, RingState& R) {
-  if (R.U == U) return;
+// the ring geometry changes with the tile width: every stage must be drained before the region is re-cut
+__device__ __forceinline__ void ring_set_geometry(int nbc, SmemTail& S, RingState& R) {
+  if (R.nbc == nbc) return;
   for (uint32_t q = 0; q < (uint32_t)kNBBar; ++q)
     if (R.pending >> q & 1u) {
       mbar_wait(&S.b_empty[q], R.empty_par >> q & 1u);
@@ -622,87 +386,88 @@ __device__ __forceinline__ void ring_set_geometry(int U, SmemTail& S, RingState&
       R.pending &= ~(1u << q);
     }
   R.next = 0;
-  R.U = U;
+  R.nbc = nbc;
+}
+// weight chunk c of a tile -> next ring stage: hi tiles of the tile's blocks, then their lo tiles
+__device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigned char* Bs, SmemTail& S, RingState& R) {
+  const uint32_t nbs = 8u / (uint32_t)nbc;
+  const uint32_t s = R.next;
+  R.next = (s + 1 == nbs) ? 0u : s + 1;
+  if (R.pending >> s & 1u) {                         // MMAs that read this stage must be done
+    mbar_wait(&S.b_empty[s], R.empty_par >> s & 1u);
+    R.empty_par ^= 1u << s;
+    R.pending &= ~(1u << s);
+  }
+  mbar_expect_tx(&S.b_full[s], (uint32_t)T.ncb * kBlkBytes);
+  unsigned char* stg = Bs + (size_t)s * nbc * kBlkBytes;
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(T.img);
+  for (int b = 0; b < T.ncb; ++b) {
+    const unsigned char* src = img + ((size_t)(T.cb0 + b) * T.nck + c) * kBlkBytes;
+    bulk_g2s(stg + (size_t)b * (kBlkBytes / 2), src, kBlkBytes / 2, &S.b_full[s]);
+    bulk_g2s(stg + (size_t)nbc * (kBlkBytes / 2) + (size_t)b * (kBlkBytes / 2), src + kBlkBytes / 2, kBlkBytes / 2, &S.b_full[s]);
+  }
 }
 
-__device__ __forceinline__ void issuer_tile(const SweepP& P, const Tile& T, int U, unsigned char* As, unsigned char* Bs, SmemTail& S,
-                                            uint32_t tmem, uint32_t ja, RingState& R, long long* tr, const Tile* nextT, int nextU) {
-  long long i_b = 0, i_a = 0, i_issue = 0, t0 = tr ? clock64() : 0;
-  const BSrc b = make_bsrc(P, T, U);
-  const int nbs = b.nbs;
-  const uint32_t idesc3 = tc::instr_desc_f16(128, 3 * U), idesc2 = tc::instr_desc_f16(128, 2 * U), idesc1 = tc::instr_desc_f16(128, U);
-
+__device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
+                                            uint32_t ja, RingState& R, const Tile* nextT, int next_nbc) {
+  const int nbs = 8 / nbc;
+  const uint32_t idesc = tc::instr_desc_f16(128, 64 * T.ncb);
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
-  // was still computing, or before the grid barrier)
-  if (R.pre == 0) ring_set_geometry(U, S, R);
+  // was still computing, or before a grid barrier)
+  if (R.pre == 0) ring_set_geometry(nbc, S, R);
   const uint32_t first = R.pre ? R.pre_first : R.next;
-  const int npre = min(nbs, T.nchunks);
-  for (int c = (int)R.pre; c < npre; ++c) ring_load(b, c, Bs, S, R);
+  const int npre = min(nbs, T.nck);
+  for (int c = (int)R.pre; c < npre; ++c) ring_load(T, nbc, c, Bs, S, R);
   R.pre = 0;
 #pragma unroll 1
-  for (int c = 0; c < T.nchunks; ++c) {
+  for (int c = 0; c < T.nck; ++c) {
     const uint32_t s = (first + (uint32_t)c) % (uint32_t)nbs;
     mbar_wait(&S.b_full[s], R.full_par >> s & 1u);
     R.full_par ^= 1u << s;
-    if (tr) { const long long t1 = clock64(); i_b += t1 - t0; t0 = t1; }
-    const uint32_t sb = smem_u32(Bs + (size_t)s * b.bstage);
-    const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + 3u * (uint32_t)U * tc::ROW_BYTES);
+    const uint32_t sb = smem_u32(Bs + (size_t)s * nbc * kBlkBytes);
+    const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)nbc * (kBlkBytes / 2));
 #pragma unroll 1
     for (int st = 0; st < T.nst; ++st) {
       const uint32_t j = ja + (uint32_t)(c * T.nst + st);
       const uint32_t stage = j % kNAS, use = j / kNAS;
       mbar_wait(&S.a_full[stage], use & 1u);
       tc::fence_after_sync();
-      if (tr) { const long long t1 = clock64(); i_a += t1 - t0; t0 = t1; }
       const uint32_t sa = smem_u32(As + (size_t)stage * kAStageBytes);
       const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + 128 * tc::ROW_BYTES);
-      const uint32_t tm = tmem + (uint32_t)(st * 4 * U);
-      if (c < T.nci) {                                  // input part: columns [0, 3U) = n_in | r | z
+      const uint32_t tm = tmem + (uint32_t)(st * 64 * nbc);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc3, c == 0 && ks == 0);
-      } else {                                          // hidden part: columns [U, 4U) = r | z | n_hid
-        const uint32_t tmh = tm + (uint32_t)U;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          if (c == T.nci && ks == 0) {                  // first touch of n_hid: overwrite it, keep accumulating r | z
-            const uint64_t nrow = (uint64_t)((2u * (uint32_t)U * tc::ROW_BYTES) >> 4);
-            tc::mma_f16(tmh, ah, bh, idesc2, 1u);
-            tc::mma_f16(tmh + 2u * (uint32_t)U, ah, bh + nrow, idesc1, 0u);
-            tc::mma_f16(tmh, al, bh, idesc3, 1u);
-            tc::mma_f16(tmh, ah, bl, idesc3, 1u);
-          } else {
-            tc::mma3_f16(tmh, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc3, false);
-          }
-        }
-      }
+      for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
       tc::commit(&S.a_empty[stage]);
-      if (tr) { const long long t1 = clock64(); i_issue += t1 - t0; t0 = t1; }
     }
     tc::commit(&S.b_empty[s]);
     R.pending |= 1u << s;
     // refill: chunk c + nbs - 1 goes where chunk c - 1 was (its MMAs precede the ones just issued)
-    if (c >= 1 && c + nbs - 1 < T.nchunks) ring_load(b, c + nbs - 1, Bs, S, R);
+    if (c >= 1 && c + nbs - 1 < T.nck) ring_load(T, nbc, c + nbs - 1, Bs, S, R);
   }
   tc::commit(&S.acc_full);
-  if (tr) { tr[14] = i_a; tr[15] = i_issue; (void)i_b; }
   // weights are constants: put the first chunks of this CTA's NEXT tile in flight now — they land while the current
-  // accumulators drain, the epilogue runs and (for the first tile of the next step) the grid barrier is crossed
+  // accumulators drain, the epilogue runs and (for the first tile of the next proj phase) the gate phase runs
   if (nextT) {
-    ring_set_geometry(nextU, S, R);
-    const BSrc nb = make_bsrc(P, *nextT, nextU);
+    ring_set_geometry(next_nbc, S, R);
     R.pre_first = R.next;
-    const int n2 = min(nb.nbs, nextT->nchunks);
-    for (int c = 0; c < n2; ++c) ring_load(nb, c, Bs, S, R);
+    const int n2 = min(8 / next_nbc, nextT->nck);
+    for (int c = 0; c < n2; ++c) ring_load(*nextT, next_nbc, c, Bs, S, R);
     R.pre = (uint32_t)n2;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// step tables: the segments (d, i, l = s - i) of a wavefront step, their tiling and this CTA's share of the tiles
+// step tables. Proj phase -1 projects X (segments = directions, all N rows); proj phase s >= 0 projects the rows the
+// gate phase of step s has just produced (segments (d, i, l = s - i)).
 // ------------------------------------------------------------------------------------------------------------
 struct TileIt { int q, t; };
 
+__device__ __forceinline__ int seg_blocks(const SweepP& P, int s, int q) {      // 64-column blocks of segment q's projection
+  const int mb = P.Mc / 64;
+  if (s < 0) return mb;                                 // X -> Gi^0
+  const int i = q % P.layers;
+  return (i + 1 < P.layers) ? 2 * mb : mb;              // H^i -> P^i [, Gi^{i+1}]
+}
 __device__ __forceinline__ bool tile_advance(const StepTab& tb, int nseg, int rank, int G, TileIt& it) {
   if (it.t >= 0) it.t += G;
   while (it.q < nseg) {
@@ -716,46 +481,63 @@ __device__ __forceinline__ bool tile_advance(const StepTab& tb, int nseg, int ra
 }
 __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, int s, const TileIt& it) {
   const Seg g = tb.seg[it.q];
-  const int NU = (tb.U == 64) ? P.NT : P.NG;
+  const int nblk = seg_blocks(P, s, it.q);
+  const int ncbt = ceil_div(nblk, tb.nbc);              // column tiles per row tile
   const int rows_per = 128 * tb.nst;
+  const int rt = it.t / ncbt, ctile = it.t - rt * ncbt;
   Tile T;
-  const int rt = it.t / NU;
-  T.d = it.q / P.layers; T.i = it.q - T.d * P.layers;
-  T.level0 = (s - T.i == 0); T.pos0 = g.pos0;
-  T.ut = it.t - rt * NU;
+  if (s < 0) {
+    const int d = it.q;
+    T.A = P.X; T.lda = P.ldx; T.perm = P.dir[d].perm; T.img = P.lay[d][0].imgx;
+    T.out0 = P.lay[d][0].Gi; T.out1 = nullptr;
+    T.K = P.Din0; T.nck = P.nckx; T.vec = P.vec_x;
+  } else {
+    const int d = it.q / P.layers, i = it.q - d * P.layers;
+    const LayP& Lp = P.lay[d][i];
+    T.A = Lp.Hs; T.lda = P.ldh; T.perm = nullptr; T.img = Lp.imgh;
+    T.out0 = Lp.Pm; T.out1 = (i + 1 < P.layers) ? P.lay[d][i + 1].Gi : nullptr;
+    T.K = P.Hq; T.nck = P.nckh; T.vec = 1;
+  }
   T.p0 = g.pos0 + rt * rows_per;
   T.nrows = min(rows_per, g.n - rt * rows_per);
   T.nst = (T.nrows + 127) >> 7;
-  T.nci = (T.i == 0) ? P.nci0 : P.ncih;
-  T.nchunks = T.nci + (T.level0 ? 0 : P.ncih);
+  T.cb0 = ctile * tb.nbc;
+  T.ncb = min(tb.nbc, nblk - T.cb0);
   return T;
 }
 // all threads; two __syncthreads inside
-__device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg, int G) {
+__device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg_max, int G) {
   const int tid = threadIdx.x;
-  if (tid < nseg) {
-    const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
+  const int nseg = (s < 0) ? P.dirs : nseg_max;
+  if (tid < kMaxSeg) {
     Seg g = {0, 0, 0, 0};
-    if (l >= 0 && l < L) {
-      g.pos0 = P.dir[d].lvl_off[l];
-      g.n = max(0, P.dir[d].lvl_off[l + 1] - g.pos0);
+    if (tid < nseg) {
+      if (s < 0) g.n = P.N;
+      else {
+        const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
+        // the last level's states have no successors: only the next layer's input projection is still needed
+        const bool needed = (l >= 0 && l < L) && (l + 1 < L || i + 1 < P.layers);
+        if (needed) {
+          g.pos0 = P.dir[d].lvl_off[l];
+          g.n = max(0, P.dir[d].lvl_off[l + 1] - g.pos0);
+        }
+      }
     }
     tb.seg[tid] = g;
   }
   __syncthreads();
   if (tid == 0) {
-    int t64 = 0;
-    for (int q = 0; q < nseg; ++q) t64 += ceil_div(tb.seg[q].n, 128) * P.NT;
-    const int U = (4 * t64 >= G) ? 64 : 16;
-    const int nst = (U == 64 && t64 >= 2 * G) ? 2 : 1;
-    const int NU = (U == 64) ? P.NT : P.NG;
+    int t64 = 0;                                        // work in units of 128 rows x 64 columns
+    for (int q = 0; q < nseg; ++q) t64 += ceil_div(tb.seg[q].n, 128) * seg_blocks(P, s, q);
+    const int nbc = (t64 >= 4 * G) ? 4 : (t64 >= 2 * G) ? 2 : 1;
+    const int nst = (nbc == 4 && t64 >= 8 * G) ? 2 : 1;
     int base_ = 0;
-    for (int q = 0; q < nseg; ++q) {
-      tb.seg[q].ntile = ceil_div(tb.seg[q].n, 128 * nst) * NU;
+    for (int q = 0; q < kMaxSeg; ++q) {
+      tb.seg[q].ntile = (q < nseg) ? ceil_div(tb.seg[q].n, 128 * nst) * ceil_div(seg_blocks(P, s, q), nbc) : 0;
       tb.seg[q].base = base_;
       base_ += tb.seg[q].ntile;
     }
-    tb.U = U; tb.nst = nst;
+    tb.nbc = nbc; tb.nst = nst;
   }
   __syncthreads();
 }
@@ -785,49 +567,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   const int nsteps = ok ? L + P.layers - 1 : 0;
   const int nseg = P.dirs * P.layers;
   const int G = (int)gridDim.x, rank = (int)blockIdx.x;
-  uint32_t ja = 0, ct = 0;
+  uint32_t ja = 0, ct = 0;                     // operand-ring items and tiles processed so far (mbarrier phases)
   RingState R = {0u, 0u, 0u, 0u, 0u, 0u, 0};
   unsigned int nbar = 0;
-  if (nsteps > 0) build_step_table(P, S.tab[0], 0, L, nseg, G);
+  if (nsteps > 0) build_step_table(P, S.tab[1], -1, L, nseg, G);      // proj phase s uses tab[s & 1]; -1 & 1 == 1
 
+  // gate phase of step s (s >= 0), then proj phase s (s = -1: X)
 #pragma unroll 1
-  for (int s = 0; s < nsteps; ++s) {
-    long long* tr = P.trace ? P.trace + ((size_t)s * 256 + blockIdx.x) * 16 : nullptr;
-    if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; tr[8] = tr[9] = tr[10] = tr[11] = 0; }
-    // the table of step s was built during step s - 1 (level offsets are constants); build the one of step s + 1 now so
-    // that the issuer can look across the grid barrier
+  for (int s = -1; s < nsteps; ++s) {
+    long long* tr = P.trace ? P.trace + ((size_t)(s + 1) * 256 + blockIdx.x) * 16 : nullptr;
+    if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; tr[8] = tr[9] = 0; }
+    if (s >= 0) {
+      // ---------------- gate phase of step s ----------------
+      const int W = G * kBuilderWarps;
+      if (warp < kBuilderWarps) {
+        int rbase = 0;
+        for (int q = 0; q < nseg; ++q) {
+          const int d = q / P.layers, i = q - d * P.layers, l = s - i;
+          if (l < 0 || l >= L) continue;
+          const DirP& D = P.dir[d];
+          const int pos0 = D.lvl_off[l], n = D.lvl_off[l + 1] - pos0;
+          // rows of the step are dealt to the warps of the grid, CTA-minor, continuing across segments
+          int r = ((warp * G + rank) - rbase % W + W) % W;
+          for (; r < n; r += W) {
+            if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane);
+            else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane);
+          }
+          rbase += n;
+        }
+      }
+      if (tr && tid == 0) tr[8] = clock64();
+      if (s + 1 < nsteps) grid_barrier(P.bar, ++nbar * (unsigned int)G);   // the last step's projection is empty
+      if (tr && tid == 0) tr[9] = clock64();
+    }
+    // ---------------- proj phase s ----------------
+    // the table of this phase was built one phase earlier (level offsets are constants); build the next one now so that
+    // the issuer can look across the barriers
     const StepTab& tb = S.tab[s & 1];
     StepTab& tbn = S.tab[(s + 1) & 1];
     const bool has_next = s + 1 < nsteps;
     if (has_next) build_step_table(P, tbn, s + 1, L, nseg, G);
-    const int U = tb.U;
+    const int nseg_now = (s < 0) ? P.dirs : nseg;
     int my_tiles = 0;
     TileIt it = {0, -1};
-    bool more = tile_advance(tb, nseg, rank, G, it);
+    bool more = tile_advance(tb, nseg_now, rank, G, it);
 #pragma unroll 1
     while (more) {
       const Tile T = make_tile(P, tb, s, it);
-      more = tile_advance(tb, nseg, rank, G, it);
+      more = tile_advance(tb, nseg_now, rank, G, it);
       if (warp < kBuilderWarps) {
-        builder_tile(P, T, U, As, S, tmem, ja, ct, my_tiles == 0 ? tr : nullptr);
+        builder_tile(P, T, As, S, tmem, ja, ct, 64 * tb.nbc, my_tiles == 0 ? tr : nullptr);
       } else if (lane == 0) {
         Tile N;
-        int nU = U;
+        int nn = tb.nbc;
         bool hn = more;
         if (more) N = make_tile(P, tb, s, it);
         else if (has_next) {
           TileIt it2 = {0, -1};
           hn = tile_advance(tbn, nseg, rank, G, it2);
-          if (hn) { N = make_tile(P, tbn, s + 1, it2); nU = tbn.U; }
+          if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
         }
-        issuer_tile(P, T, U, As, Bs, S, tmem, ja, R, my_tiles == 0 ? tr : nullptr, hn ? &N : nullptr, nU);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, R, hn ? &N : nullptr, nn);
       }
       __syncwarp();
-      ja += (uint32_t)(T.nchunks * T.nst);
+      ja += (uint32_t)(T.nck * T.nst);
       ct += 1;
       ++my_tiles;
     }
-    if (tr && tid == 0) { tr[4] = clock64(); tr[6] = my_tiles; tr[7] = U | ((128 * tb.nst) << 8); }
+    if (tr && tid == 0) { tr[4] = clock64(); tr[6] = my_tiles; tr[7] = (64 * tb.nbc) | ((128 * tb.nst) << 12); }
     if (has_next) grid_barrier(P.bar, ++nbar * (unsigned int)G);
     if (tr && tid == 0) tr[5] = clock64();
   }
@@ -841,15 +648,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
 using namespace dagnn;
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
-constexpr int kMaxGrid = 160;     // CTAs (= SMs) the per-CTA scratch is sized for
-static size_t heavy_bytes(int H) { return align256((size_t)kMaxGrid * kMaxRows * round_up(H, 4) * sizeof(float)); }
 
 extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E) {
   if (dirs < 1 || dirs > DAGNN_MAX_DIRS || layers < 1 || layers > DAGNN_MAX_LAYERS || Din < 1 || H < 1 || N < 0 || E < 0) return 0;
-  const size_t nskp = (size_t)round_up(ceil_div(H, 16), 4);
-  return 256 + heavy_bytes(H) + (size_t)dirs * layers * (align256((size_t)N * nskp * sizeof(float)) + align256((size_t)E * sizeof(float)));
+  const size_t Mc = (size_t)round_up(3 * round_up(H, 4), 64);
+  // per (direction, layer): key scores [N], hidden projection P [N, Mc], input projection Gi [N, Mc]
+  return 256 + (size_t)dirs * layers * (align256((size_t)N * sizeof(float)) + 2 * align256((size_t)N * Mc * sizeof(float)));
 }
-extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)max_steps * 256 * 16 * sizeof(long long); }
+extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)(max_steps + 1) * 256 * 16 * sizeof(long long); }
 
 extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -865,21 +671,20 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
     return set_err(DAGNN_E_WORKSPACE, "sweep: workspace too small (dagnn_sweep_workspace_bytes)");
   if (H < 1 || H > 4096) return set_err(DAGNN_E_UNSUPPORTED, "sweep: hidden size %d not in [1,4096]", H);
   if (A->nvid < 0) return set_err(DAGNN_E_INVALID, "sweep: nvid");
-  DagnnPackLayout lay0, layL;
-  if (int rc = dagnn_pack_layout(A->Din, H, A->nvid, &lay0)) return rc;
-  if (int rc = dagnn_pack_layout(H, H, A->nvid, &layL)) return rc;
+  if (S->N >= (1ll << 31)) return set_err(DAGNN_E_UNSUPPORTED, "sweep: more than 2^31 nodes");
   SweepP P;
   memset(&P, 0, sizeof(P));
-  P.dirs = dirs; P.layers = layers; P.H = H; P.Hq = round_up(H, 4); P.nvid = A->nvid;
-  P.use_ea = A->use_edge_attr; P.Din0 = A->Din; P.nci0 = lay0.Kin64 / 64; P.ncih = lay0.Kh64 / 64;
-  P.NG = lay0.NG; P.NT = lay0.NT; P.nskp = round_up(lay0.NG, 4);
+  DagnnPackLayout lay[DAGNN_MAX_LAYERS];
+  for (int i = 0; i < layers; ++i)
+    if (int rc = dagnn_pack_layout(i == 0 ? A->Din : H, H, A->nvid, i == 0, i + 1 == layers, &lay[i])) return rc;
+  P.dirs = dirs; P.layers = layers; P.H = H; P.Hq = lay[0].Hq; P.Mc = lay[0].Mc; P.HP = lay[0].HP; P.nvid = A->nvid;
+  P.use_ea = A->use_edge_attr; P.Din0 = A->Din; P.nckx = lay[0].Kin64 / 64; P.nckh = lay[0].Kh64 / 64;
   P.vec_x = ((A->ldx & 3) == 0 && (A->Din & 3) == 0 && ((uintptr_t)A->X & 15) == 0) ? 1 : 0;
+  P.N = (int)S->N;
   P.ldh = A->ldh; P.ldx = A->ldx; P.X = A->X; P.summary = S->summary; P.bar = static_cast<unsigned int*>(A->workspace);
   P.trace = static_cast<long long*>(A->trace);
   char* ws = static_cast<char*>(A->workspace) + 256;
-  P.heavy = reinterpret_cast<float*>(ws);
-  ws += heavy_bytes(H);
-  const size_t skp_bytes = align256((size_t)S->N * P.nskp * sizeof(float)), alpha_bytes = align256((size_t)S->E * sizeof(float));
+  const size_t sk_bytes = align256((size_t)S->N * sizeof(float)), pm_bytes = align256((size_t)S->N * P.Mc * sizeof(float));
   for (int d = 0; d < dirs; ++d) {
     DAGNN_REQUIRE(S->perm[d] && S->rowptr[d] && S->lvl_off[d] && (S->E == 0 || S->col[d]), "sweep: schedule arrays");
     DAGNN_REQUIRE(!A->use_edge_attr || S->E == 0 || S->eattr[d], "sweep: schedule carries no edge attributes");
@@ -888,14 +693,15 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
     for (int i = 0; i < layers; ++i) {
       DAGNN_REQUIRE(A->Hs[d][i] && ((uintptr_t)A->Hs[d][i] & 15) == 0, "sweep: state buffers must be 16-byte aligned");
       DAGNN_REQUIRE(A->packed[d][i] && ((uintptr_t)A->packed[d][i] & 15) == 0, "sweep: packed params must be 16-byte aligned");
-      const DagnnPackLayout& L = i == 0 ? lay0 : layL;
+      const DagnnPackLayout& L = lay[i];
       const float* pk = A->packed[d][i];
       LayP& q = P.lay[d][i];
       q.Hs = A->Hs[d][i]; q.bias = pk + L.bias_off; q.wk = pk + L.wk_off; q.attnc = pk + L.attnc_off; q.vidk = pk + L.vidk_off;
-      q.img16 = reinterpret_cast<const __half*>(pk + L.img16_off);
-      q.img64 = reinterpret_cast<const __half*>(pk + L.img64_off);
-      q.skp = reinterpret_cast<float*>(ws); ws += skp_bytes;
-      q.alpha = reinterpret_cast<float*>(ws); ws += alpha_bytes;
+      q.imgh = reinterpret_cast<const __half*>(pk + L.imgh_off);
+      q.imgx = i == 0 ? reinterpret_cast<const __half*>(pk + L.imgx_off) : nullptr;
+      q.sk = reinterpret_cast<float*>(ws); ws += sk_bytes;
+      q.Pm = reinterpret_cast<float*>(ws); ws += pm_bytes;
+      q.Gi = reinterpret_cast<float*>(ws); ws += pm_bytes;
     }
   }
 
@@ -911,7 +717,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
     if (!coop) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device has no cooperative launch");
     sm_count[dev] = n;
   }
-  const int G = sm_count[dev] < kMaxGrid ? sm_count[dev] : kMaxGrid;
+  const int G = sm_count[dev];
   DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 16, st));
   void* kargs[] = {(void*)&P};
   DAGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(G), dim3(kThreads), kargs, kSmemBytes, st));

@@ -199,9 +199,9 @@ class PackedParams(object):
         self.layouts: List[DagnnPackLayout] = []
 
     @staticmethod
-    def layout(Din: int, H: int, nvid: int) -> DagnnPackLayout:
+    def layout(Din: int, H: int, nvid: int, first: bool, last: bool) -> DagnnPackLayout:
         L = DagnnPackLayout()
-        check(lib().dagnn_pack_layout(Din, H, nvid, C.byref(L)), "dagnn_pack_layout")
+        check(lib().dagnn_pack_layout(Din, H, nvid, int(first), int(last), C.byref(L)), "dagnn_pack_layout")
         return L
 
     def update(self, cells, aggrs, Din: int, H: int, nvid: int, use_edge_attr: bool, device):
@@ -222,7 +222,9 @@ class PackedParams(object):
             for i in range(len(cells[d])):
                 cell, ag = cells[d][i], aggrs[d][i]
                 din = Din if i == 0 else H
-                L = self.layout(din, H, nvid)
+                nl = len(cells[d])
+                L = self.layout(din, H, nvid, i == 0, i + 1 == nl)
+                nxt = cells[d][i + 1].weight_ih.detach().contiguous() if i + 1 < nl else None
                 for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag.attn_lin.weight):
                     _req_cuda(p, "parameter", torch.float32)
                 aw = ag.attn_lin.weight.detach().contiguous()
@@ -235,7 +237,7 @@ class PackedParams(object):
                 blob = torch.empty(int(L.total_floats), device=device, dtype=torch.float32)
                 check(lib().dagnn_pack_params_f32(_ptr(cell.weight_ih.detach().contiguous()), _ptr(cell.weight_hh.detach().contiguous()),
                                                   _ptr(cell.bias_ih.detach().contiguous()), _ptr(cell.bias_hh.detach().contiguous()),
-                                                  _ptr(aw), int(Dq), _ptr(ew), C.byref(L), _ptr(blob), _stream()),
+                                                  _ptr(aw), int(Dq), _ptr(ew), _ptr(nxt), C.byref(L), _ptr(blob), _stream()),
                       "dagnn_pack_params_f32")
                 row.append(blob)
                 if d == 0:
@@ -284,7 +286,7 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
         a.trace = trace.data_ptr()
     check(lib().dagnn_sweep_forward_f32(C.byref(a), _stream()), "dagnn_sweep_forward_f32")
     if trace is not None:
-        return Hs, trace.view(trace_steps, 256, 16)
+        return Hs, trace.view(-1, 256, 16)
     return Hs
 
 

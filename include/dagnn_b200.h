@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 3
+#define DAGNN_ABI_VERSION 4
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -93,10 +93,12 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
 
 /* ---------------------------------------------------------------------------------------------------------
  * Parameter packing for one (direction, layer): GRU weights -> fp16 hi/lo split, pre-swizzled shared-memory images
- * that the level kernel bulk-copies and feeds to tcgen05.mma; attention vector -> key part + edge-type coefficients.
+ * that the projection GEMM bulk-copies and feeds to tcgen05.mma; attention vector -> key part + edge-type coefficients.
  * Sources: nn.GRUCell weight_ih [3H,Din], weight_hh [3H,H], bias_ih/bias_hh [3H]   (dagnn.py:79-81),
  *          attn_lin.weight [1, Dq + H (+nvid)] (dagnn.py:359; dvae/dagnn.py:47-48,357),
- *          edge_encoder.weight [H,2] (dagnn.py:356) or NULL.
+ *          edge_encoder.weight [H,2] (dagnn.py:356) or NULL,
+ *          weight_ih of the NEXT stacked layer [3H,H] (NULL for the last layer): the state of layer i is the operand of
+ *          both W_hh^i (its own recurrence) and W_ih^{i+1} (the next layer's input), so the two ride in one image.
  * The query part of attn_lin (first Dq columns), attn_lin.bias and edge_encoder.bias add the same constant
  * to every in-edge score of a node and cancel in the softmax, so they are not packed.
  * Layout of `packed` (4-byte units), all offsets from dagnn_pack_layout():
@@ -104,24 +106,25 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
  *   wk    [HP]                  key weights on the hidden state
  *   attnc [4]                   {wk.W_e[:,0], wk.W_e[:,1], 0, 0}
  *   vidk  [nvid]                key weights on the one-hot vertex id (D-VAE NA), nvid may be 0
- *   img16 [NG][nc][hi,lo][48 rows][64 halfs]    NG = ceil(H/16) unit groups, nc = (Kin64 + Kh64)/64 k chunks
- *   img64 [NT][nc][hi,lo][192 rows][64 halfs]   NT = ceil(H/64) unit tiles
- *         K-major SWIZZLE_128B images (dagnn_b200/csrc/tc.cuh) of w = hi + lo, hi = rn_f16(w), lo = rn_f16(w - hi);
- *         rows = [n|r|z] x U units for the input chunks, [r|z|n] x U units for the hidden chunks (U = 16 / 64).
+ *   imgx  [Mc/64][Kin64/64][hi,lo][64 rows][64 halfs]        W_ih over the layer input (first layer only)
+ *   imgh  [(1|2) Mc/64][Kh64/64][hi,lo][64 rows][64 halfs]   [W_hh ; W_ih of the next layer] over this layer's state
+ *         column c of a matrix = gate * Hq + unit (gates r, z, n; Hq = roundup(H,4)), zero-padded to Mc = roundup(3 Hq, 64);
+ *         K-major SWIZZLE_128B tiles (dagnn_b200/csrc/tc.cuh) of w = hi + lo, hi = rn_f16(w), lo = rn_f16(w - hi).
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnPackLayout {
   int32_t Din, H, nvid;
-  int32_t Kin64, Kh64;                 /* K of the input / hidden part padded to the 64-wide chunk             */
-  int32_t NG, NT, HP;                  /* 16-unit groups, 64-unit tiles, padded unit count                     */
-  int64_t bias_off, wk_off, attnc_off, vidk_off, img16_off, img64_off, total_floats;
+  int32_t first_layer, last_layer;
+  int32_t Hq, Mc;                      /* roundup(H,4); padded columns of one projected matrix                 */
+  int32_t Kin64, Kh64, HP;             /* K of the input / state operand padded to the 64-wide chunk; padded units */
+  int64_t bias_off, wk_off, attnc_off, vidk_off, imgx_off, imgh_off, total_floats;
 } DagnnPackLayout;
 
-int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, DagnnPackLayout* out);
+int dagnn_pack_layout(int32_t Din, int32_t H, int32_t nvid, int32_t first_layer, int32_t last_layer, DagnnPackLayout* out);
 
 /* `packed` must be 16-byte aligned (the images are bulk-copied into swizzled shared memory). */
 int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const float* bias_ih,
                           const float* bias_hh, const float* attn_w, int32_t Dq, const float* edge_w,
-                          const DagnnPackLayout* layout, float* packed, void* stream);
+                          const float* weight_ih_next, const DagnnPackLayout* layout, float* packed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * The level sweep (the hot path): for every direction d, level l (sequential) and stacked layer i,

@@ -24,27 +24,28 @@ def test_header_symbols_are_exported_and_bound(built_lib):
         assert hasattr(raw, name), "libdagnn_sm100.so does not export %s" % name
         assert name in _lib.EXPORTS, "%s is declared in the header but has no ctypes binding" % name
     assert sorted(_lib.EXPORTS) == declared
-    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 3
+    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_pack_layout_and_workspace_queries(built_lib):
     from dagnn_b200 import _lib
     L = _lib.DagnnPackLayout()
-    assert built_lib.dagnn_pack_layout(256, 256, 0, C.byref(L)) == 0
-    assert (L.Kin64, L.Kh64, L.NG, L.NT, L.HP) == (256, 256, 16, 4, 256)
-    nc = (L.Kin64 + L.Kh64) // 64
-    assert L.img64_off - L.img16_off == L.NG * nc * 2 * 48 * 64 // 2          # fp16 images counted in 4-byte units
-    assert L.total_floats - L.img64_off == L.NT * nc * 2 * 192 * 64 // 2
-    assert L.img16_off % 256 == 0
-    assert built_lib.dagnn_pack_layout(8, 501, 8, C.byref(L)) == 0            # D-VAE NA: Din = 8, H = 501, 8 vertex-id columns
-    assert (L.Kin64, L.Kh64, L.NG, L.NT, L.HP) == (64, 512, 32, 8, 512)
-    assert built_lib.dagnn_pack_layout(0, 16, 0, C.byref(L)) != 0             # bad argument -> error code + message
+    assert built_lib.dagnn_pack_layout(256, 256, 0, 1, 0, C.byref(L)) == 0     # first of several layers
+    assert (L.Hq, L.Mc, L.Kin64, L.Kh64, L.HP) == (256, 768, 256, 256, 256)
+    assert L.imgh_off - L.imgx_off == (L.Mc // 64) * (L.Kin64 // 64) * 2 * 4096 // 2      # fp16 images counted in 4-byte units
+    assert L.total_floats - L.imgh_off == 2 * (L.Mc // 64) * (L.Kh64 // 64) * 2 * 4096 // 2   # [W_hh ; W_ih of the next layer]
+    assert L.imgx_off % 256 == 0
+    assert built_lib.dagnn_pack_layout(256, 256, 0, 0, 1, C.byref(L)) == 0     # last layer: no next-layer block, no input image
+    assert L.imgh_off == L.imgx_off and L.total_floats - L.imgh_off == (L.Mc // 64) * (L.Kh64 // 64) * 2 * 4096 // 2
+    assert built_lib.dagnn_pack_layout(8, 501, 8, 1, 0, C.byref(L)) == 0        # D-VAE NA: Din = 8, H = 501, 8 vertex-id columns
+    assert (L.Hq, L.Mc, L.Kin64, L.Kh64, L.HP) == (504, 1536, 64, 512, 512)
+    assert built_lib.dagnn_pack_layout(0, 16, 0, 1, 1, C.byref(L)) != 0         # bad argument -> error code + message
     assert b"pack_layout" in built_lib.dagnn_last_error()
     ws = built_lib.dagnn_sweep_workspace_bytes(2, 2, 256, 256, 16478, 24491)
-    assert ws >= 256 + 4 * (16478 * 16 * 4 + 24491 * 4)
+    assert ws >= 256 + 4 * (16478 * 4 + 2 * 16478 * 768 * 4)
     assert built_lib.dagnn_sweep_workspace_bytes(3, 2, 256, 256, 10, 10) == 0   # dirs out of range
     assert built_lib.dagnn_schedule_workspace_bytes(1000, 2000, 256) > 0
-    assert built_lib.dagnn_sweep_trace_bytes(10) == 10 * 256 * 16 * 8
+    assert built_lib.dagnn_sweep_trace_bytes(10) == 11 * 256 * 16 * 8
 
 
 def test_no_cpu_path():

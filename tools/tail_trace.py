@@ -1,0 +1,22 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import bench
+from dagnn_b200 import runtime as rt, _lib
+wl = bench.WORKLOADS["c2"]
+_lib.build_library()
+dev = torch.device("cuda:0")
+B = bench.build_workload(wl, 1); m = bench.build_module(wl).to(dev); G = B.to(dev)
+with torch.no_grad():
+    X, Hs, sched = m.node_states(G); packed = m._pack(dev)
+    L = sched.num_levels[0]; steps = L + 1
+    for _ in range(3):
+        Hs, tr = rt.sweep(sched, X, packed, 256, 256, 2, 0, True, trace_steps=steps)
+    torch.cuda.synchronize()
+tr = tr.cpu().numpy()[:, :148, :].astype(np.float64) / 1965.0
+for s in (45, 50, 55, 60, 64):
+    t = tr[s]
+    for c in (0, 1, 17, 40):
+        if t[c, 6] * 1965 > 0:
+            print("step %d cta %d: rel us: tile-start %.2f | rp-loaded %.2f | scores %.2f | softmax %.2f | pre-done %.2f | b1-loads-issued %.2f | b1-arrived %.2f | build-done %.2f || tr1 %.2f acc %.2f epi-done %.2f all %.2f barrier %.2f" % (
+                s, c, t[c, 8], t[c, 9], t[c, 10], t[c, 11], t[c, 12], t[c, 13], t[c, 14], t[c, 15], t[c,1]-t[c,0], t[c,2]-t[c,0], t[c,3]-t[c,0], t[c,4]-t[c,0], t[c,5]-t[c,0]))

@@ -22,30 +22,28 @@ with torch.no_grad():
     for _ in range(3):
         Hs, tr = rt.sweep(sched, X, packed, wl["emb"], wl["hid"], wl["layers"], nvid, wl["kind"] == "code2", trace_steps=steps)
     torch.cuda.synchronize()
-tr = tr.cpu().numpy()[:, :148, :]
+tr = tr.cpu().numpy()[:, :148, :].astype(np.float64)
 MHZ = 1965.0
 lo = sched.lvl_off_host
-print("all times in us. first tile of CTA 0: pre = rowptr + softmax weights, wait = free operand stage, build = gather+split+store, "
-      "hand = proxy fence + arrive; issuer: wB = wait weights, wA = wait operands, iss = MMA issue")
-print("step | level sizes | U rows | tiles/CTA | build  acc  epi  rest (max over CTAs) | step || slowest CTA: pre wait slow+store hand comb pref | wA iss")
+print("all times in us, max over CTAs unless noted. row s = gate phase of step s, then projection of the rows it produced (row -1: X)")
+print("step | level sizes | gate(max) gate(med) bar1 | cols rows tiles/CTA | build  acc  epi  rest | bar2(min) | step")
 tot = 0
-for s in range(steps):
-    t = tr[s].astype(np.float64)
-    n0 = [int(lo[d][s + 1] - lo[d][s]) if s < L else 0 for d in range(len(lo))]
+for k in range(steps + 1):
+    s = k - 1
+    t = tr[k]
+    n0 = [int(lo[d][s + 1] - lo[d][s]) if 0 <= s < L else 0 for d in range(len(lo))]
     act = t[:, 6] > 0
-    g = np.where(act, (t[:, 1] - t[:, 0]) / MHZ, 0); bw = np.where(act, (t[:, 2] - t[:, 1]) / MHZ, 0)
+    gate = (t[:, 8] - t[:, 0]) / MHZ if s >= 0 else np.zeros(148)
+    bar1 = (t[:, 9] - t[:, 8]) / MHZ if s >= 0 else np.zeros(148)
+    p0 = t[:, 9] if s >= 0 else t[:, 0]
+    g = np.where(act, (t[:, 1] - p0) / MHZ, 0); bw = np.where(act, (t[:, 2] - t[:, 1]) / MHZ, 0)
     pm = np.where(act, (t[:, 3] - t[:, 2]) / MHZ, 0); tl = np.where(act, (t[:, 4] - t[:, 3]) / MHZ, 0)
-    end = t[:, 5] if s + 1 < steps else t[:, 4]
+    end = np.maximum(t[:, 5], t[:, 4])
+    bar2 = (t[:, 5] - t[:, 4]) / MHZ
     stepdur = ((end - t[:, 0]) / MHZ).max()
     tot += stepdur
-    k = int(np.argmax(np.where(act, t[:, 4] - t[:, 0], -1))) if act.any() else 0     # slowest CTA of the step
     f = int(t[0, 7])
-    print("%3d | %12s | %2d %3d | %2d | %6.1f %6.1f %6.1f %7.1f | %7.1f || %5.1f %5.1f %5.1f %5.1f %5.1f %5.1f | %5.1f %5.1f" % (
-        s, n0, f & 255, f >> 8, int(t[:, 6].max()), g.max(), bw.max(), pm.max(), tl.max(), stepdur,
-        t[k, 8] / MHZ, t[k, 9] / MHZ, t[k, 10] / MHZ, t[k, 11] / MHZ, t[k, 12] / MHZ, t[k, 13] / MHZ, t[k, 14] / MHZ, t[k, 15] / MHZ))
-    if len(sys.argv) > 2 and s == int(sys.argv[2]):       # per-CTA dump of one step
-        for c in range(148):
-            print("   cta %3d tiles %d | build %.1f acc %.1f epi %.1f rest %.1f | pre %.1f wait %.1f build %.1f hand %.1f | wB %.1f wA %.1f iss %.1f stg %d" % (
-                c, int(t[c, 6]), g[c], bw[c], pm[c], tl[c], t[c, 8] / MHZ, t[c, 9] / MHZ, t[c, 10] / MHZ, t[c, 11] / MHZ, t[c, 12] / MHZ,
-                t[c, 13] / MHZ, t[c, 14] / MHZ, int(t[c, 15])))
+    print("%3d | %12s | %6.1f %6.1f %5.1f | %3d %3d %2d | %6.1f %6.1f %6.1f %6.1f | %5.1f | %7.1f" % (
+        s, n0, gate.max(), np.median(gate), bar1.min() if s >= 0 else 0, f & 4095, f >> 12, int(t[:, 6].max()), g.max(), bw.max(), pm.max(), tl.max(),
+        bar2.min(), stepdur))
 print("sum of step durations: %.1f us" % tot)
