@@ -38,6 +38,8 @@ constexpr int kBRegionBytes = 8 * kBlkBytes;             // weight ring: 2 x 4 b
 constexpr int kNBBar = 8;
 constexpr int kMaxSeg = DAGNN_MAX_DIRS * DAGNN_MAX_LAYERS;
 constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 columns
+constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (8 warps split the edge list)
+constexpr int kMaxCoop = 48;       // ... per CTA and gate phase; beyond that a warp does the node alone
 constexpr int kMaxSmem = 232448;                         // 227 KB opt-in limit per CTA on sm_100
 
 struct DirP {
@@ -81,6 +83,8 @@ struct StepTab {
 };
 struct SmemTail {
   StepTab tab[2];             // this proj phase's and the next one's segment tables
+  int coop[kMaxCoop][2];      // gate phase: (segment, position) of the nodes this CTA aggregates cooperatively
+  int ncoop;
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
   uint32_t tmem_slot;
 };
@@ -143,109 +147,282 @@ __device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
 
 // ------------------------------------------------------------------------------------------------------------
 // gate phase: one warp per node. Lane l owns the units 4 l + 128 j (+ 0..3), j < J, of a 128 J wide column pass.
+// The chain of dependent L2 round trips is what a node costs (~0.3-0.5 us each), so everything that does not depend
+// on the previous load is issued with it: row pointers + the node's own Gi row; then the in-edge list; then the key
+// scores AND the projected rows of the first in-edges together; the softmax runs while those rows are in flight.
 // ------------------------------------------------------------------------------------------------------------
+struct GateAcc {                   // per lane: sum_e alpha_e * (P_r, P_z, P_n, h) for the lane's units
+  float4 r, z, n, m;
+};
+
 template <int J>
-__device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, bool level0, int lane) {
-  const int Hq = P.Hq, Mc = P.Mc, HP = P.HP;
+struct GateRows {                  // projected + state rows of one in-edge, lane's units
+  float4 r[J], z[J], n[J], h[J];
+};
+template <int J>
+__device__ __forceinline__ void load_rows(GateRows<J>& R, const float* __restrict__ Pm, const float* __restrict__ Hs, int sp, bool on,
+                                          int Mc, long long ldh, int Hq, int ub, int lane) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* pr = Pm + (size_t)sp * Mc;
+  const float* hr = Hs + (size_t)sp * ldh;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int u = ub + 4 * lane + 128 * j;
+    R.r[j] = z4; R.z[j] = z4; R.n[j] = z4; R.h[j] = z4;
+    if (on && u < Hq) {
+      R.r[j] = ldcg4(pr + u);
+      R.z[j] = ldcg4(pr + Hq + u);
+      R.n[j] = ldcg4(pr + 2 * Hq + u);
+      R.h[j] = ldcg4(hr + u);
+    }
+  }
+}
+template <int J>
+__device__ __forceinline__ void add_rows(GateAcc (&A)[J], float a, const GateRows<J>& R) {
+#pragma unroll
+  for (int j = 0; j < J; ++j) { fma4(A[j].r, a, R.r[j]); fma4(A[j].z, a, R.z[j]); fma4(A[j].n, a, R.n[j]); fma4(A[j].m, a, R.h[j]); }
+}
+
+// score of in-edge e (lane-private): key score of the predecessor if it sits in an earlier level, else 0 — such an edge
+// keeps its softmax mass and adds a zero row — plus the edge-type / vertex-id terms
+__device__ __forceinline__ float edge_score(const SweepP& P, const DirP& D, const LayP& Lp, int e, int pos0, float ca0, float ca1,
+                                            bool use_ea, int& sp) {
+  sp = D.col[e];
+  float sc = (sp < pos0) ? __ldcg(Lp.sk + sp) : 0.f;
+  if (use_ea) {
+    const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
+    sc += ca0 * ea.x + ca1 * ea.y;
+  }
+  if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
+  return sc;
+}
+
+// GRU pointwise for the lane's units of one column pass; returns the lane's part of wk . h
+template <int J>
+__device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, int p, int ub, int lane, const GateAcc (&A)[J]) {
+  const int Hq = P.Hq, HP = P.HP;
+  const float* __restrict__ gi = Lp.Gi + (size_t)p * P.Mc;
+  float skacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int u = ub + 4 * lane + 128 * j;
+    if (u >= Hq) continue;
+    const float4 gr = ldcg4(gi + u), gz = ldcg4(gi + Hq + u), gn = ldcg4(gi + 2 * Hq + u);
+    const float4 br = __ldg(reinterpret_cast<const float4*>(Lp.bias + u));
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(Lp.bias + HP + u));
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(Lp.bias + 2 * HP + u));
+    const float4 bh = __ldg(reinterpret_cast<const float4*>(Lp.bias + 3 * HP + u));
+    const float4 wk = __ldg(reinterpret_cast<const float4*>(Lp.wk + u));
+    float4 o;
+#define DAGNN_GATE(c)                                                          \
+  {                                                                            \
+    const float rg = fast_sigmoid(gr.c + A[j].r.c + br.c);                     \
+    const float zg = fast_sigmoid(gz.c + A[j].z.c + bz.c);                     \
+    const float ng = fast_tanh(gn.c + bi.c + rg * (A[j].n.c + bh.c));          \
+    o.c = ng + zg * (A[j].m.c - ng);                                           \
+  }
+    DAGNN_GATE(x) DAGNN_GATE(y) DAGNN_GATE(z) DAGNN_GATE(w)
+#undef DAGNN_GATE
+    *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = o;
+    skacc += o.x * wk.x + o.y * wk.y + o.z * wk.z + o.w * wk.w;       // units >= H: zero weights and biases -> o = 0
+  }
+  return skacc;
+}
+
+// one warp, one node. Returns false (and does nothing) if the node has more than kCoopEdges in-edges and `may_defer`.
+template <int J>
+__device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, bool level0, int lane,
+                                         bool may_defer) {
+  const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
-  const float* __restrict__ gi = Lp.Gi + (size_t)p * Mc;
   const float* __restrict__ Pm = Lp.Pm;
   const float* __restrict__ Hs = Lp.Hs;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e0 = 0, e1 = 0;
-  float mx = 0.f, inv = 0.f;
   const bool use_ea = P.use_ea && D.eattr != nullptr;
   const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
-  // score of in-edge e (lane-private): key score of the predecessor if it sits in an earlier level, else 0 — such an edge
-  // keeps its softmax mass and adds a zero row — plus the edge-type / vertex-id terms
-  auto score = [&](int e, int& sp) {
-    sp = D.col[e];
-    float sc = (sp < pos0) ? __ldcg(Lp.sk + sp) : 0.f;
-    if (use_ea) {
-      const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
-      sc += ca0 * ea.x + ca1 * ea.y;
+  int e0 = 0, e1 = 0;
+  if (!level0) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
+  const int ne = e1 - e0;
+  if (may_defer && ne > kCoopEdges) return false;
+  float skacc = 0.f;
+  if (ne <= 32) {
+    // ---- the common case: all in-edges in one round, one lane per edge
+    int my_sp = 0;
+    float my_sc = -INFINITY;
+    if (lane < ne) my_sc = edge_score(P, D, Lp, e0 + lane, pos0, ca0, ca1, use_ea, my_sp);
+    const bool my_valid = lane < ne && my_sp < pos0;
+#pragma unroll 1
+    for (int ub = 0; ub < Hq; ub += 128 * J) {
+      GateAcc A[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) { A[j].r = z4; A[j].z = z4; A[j].n = z4; A[j].m = z4; }
+      if (ne > 0) {
+        // rows of the first in-edges go in flight before the softmax (their address needs the edge list only)
+        constexpr bool kTwo = J <= 2;                      // two in-edges in flight per lane when the registers allow it
+        GateRows<J> R0;
+        GateRows<kTwo ? J : 1> R1;
+        const int sp0 = __shfl_sync(0xffffffffu, my_sp, 0), sp1 = __shfl_sync(0xffffffffu, my_sp, 1);
+        const bool v0 = __shfl_sync(0xffffffffu, (int)my_valid, 0) != 0, v1 = __shfl_sync(0xffffffffu, (int)my_valid, 1) != 0;
+        load_rows<J>(R0, Pm, Hs, sp0, v0, Mc, ldh, Hq, ub, lane);
+        if constexpr (kTwo) load_rows<J>(R1, Pm, Hs, sp1, v1, Mc, ldh, Hq, ub, lane);
+        const float mx = warp_max(my_sc);
+        const float ex = (lane < ne) ? expf(my_sc - mx) : 0.f;
+        const float inv = 1.f / (warp_sum(ex) + 1e-16f);
+        const float my_a = my_valid ? ex * inv : 0.f;
+        add_rows<J>(A, __shfl_sync(0xffffffffu, my_a, 0), R0);
+        if constexpr (kTwo) {
+          add_rows<J>(A, __shfl_sync(0xffffffffu, my_a, 1), R1);
+          for (int q = 2; q < ne; q += 2) {
+            const float a0 = __shfl_sync(0xffffffffu, my_a, q), a1 = __shfl_sync(0xffffffffu, my_a, (q + 1) & 31);
+            const int s0 = __shfl_sync(0xffffffffu, my_sp, q), s1 = __shfl_sync(0xffffffffu, my_sp, (q + 1) & 31);
+            load_rows<J>(R0, Pm, Hs, s0, a0 != 0.f, Mc, ldh, Hq, ub, lane);
+            load_rows<J>(R1, Pm, Hs, s1, a1 != 0.f && q + 1 < ne, Mc, ldh, Hq, ub, lane);
+            add_rows<J>(A, a0, R0);
+            add_rows<J>(A, (q + 1 < ne) ? a1 : 0.f, R1);
+          }
+        } else {
+          (void)sp1; (void)v1;
+          for (int q = 1; q < ne; ++q) {
+            const float a0 = __shfl_sync(0xffffffffu, my_a, q);
+            const int s0 = __shfl_sync(0xffffffffu, my_sp, q);
+            if (a0 == 0.f) continue;
+            load_rows<J>(R0, Pm, Hs, s0, true, Mc, ldh, Hq, ub, lane);
+            add_rows<J>(A, a0, R0);
+          }
+        }
+      }
+      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
     }
-    if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
-    return sc;
-  };
-  if (!level0) {
-    e0 = D.rowptr[p];
-    e1 = D.rowptr[p + 1];
-    float sum = 0.f;
-    mx = -INFINITY;
-    for (int eb = e0; eb < e1; eb += 32) {                 // softmax statistics, 32 in-edges per round
+  } else {
+    // ---- long edge lists (a warp alone): softmax statistics first, 32 in-edges per round, then the weighted rows
+    float sum = 0.f, mx = -INFINITY;
+    for (int eb = e0; eb < e1; eb += 32) {
       const int e = eb + lane;
       int sp;
-      const float sc = (e < e1) ? score(e, sp) : -INFINITY;
+      const float sc = (e < e1) ? edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, sp) : -INFINITY;
       const float mnew = fmaxf(mx, warp_max(sc));
       sum = sum * expf(mx - mnew) + warp_sum((e < e1) ? expf(sc - mnew) : 0.f);
       mx = mnew;
     }
-    inv = (e1 > e0) ? 1.f / (sum + 1e-16f) : 0.f;
-  }
-  float skacc = 0.f;
+    const float inv = 1.f / (sum + 1e-16f);
 #pragma unroll 1
-  for (int ub = 0; ub < Hq; ub += 128 * J) {
-    float4 ar[J], az[J], an[J], am[J];
+    for (int ub = 0; ub < Hq; ub += 128 * J) {
+      GateAcc A[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { ar[j] = z4; az[j] = z4; an[j] = z4; am[j] = z4; }
-    for (int eb = e0; eb < e1; eb += 32) {
-      const int e = eb + lane;
-      int my_sp = 0;
-      float my_a = 0.f;
-      if (e < e1) {
-        const float sc = score(e, my_sp);
-        my_a = (my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
-      }
-      const int ne = min(32, e1 - eb);
-      for (int q = 0; q < ne; ++q) {
-        const float a = __shfl_sync(0xffffffffu, my_a, q);
-        const int sp = __shfl_sync(0xffffffffu, my_sp, q);
-        if (a == 0.f) continue;                            // warp-uniform
-        const float* pr = Pm + (size_t)sp * Mc;
-        const float* hr = Hs + (size_t)sp * ldh;
-        float4 vr[J], vz[J], vn[J], vh[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const int u = ub + 4 * lane + 128 * j;
-          vr[j] = z4; vz[j] = z4; vn[j] = z4; vh[j] = z4;
-          if (u < Hq) {
-            vr[j] = ldcg4(pr + u);
-            vz[j] = ldcg4(pr + Hq + u);
-            vn[j] = ldcg4(pr + 2 * Hq + u);
-            vh[j] = ldcg4(hr + u);
-          }
+      for (int j = 0; j < J; ++j) { A[j].r = z4; A[j].z = z4; A[j].n = z4; A[j].m = z4; }
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int my_sp = 0;
+        float my_a = 0.f;
+        if (e < e1) {
+          const float sc = edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, my_sp);
+          my_a = (my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
         }
-#pragma unroll
-        for (int j = 0; j < J; ++j) { fma4(ar[j], a, vr[j]); fma4(az[j], a, vz[j]); fma4(an[j], a, vn[j]); fma4(am[j], a, vh[j]); }
+        const int nq = min(32, e1 - eb);
+        for (int q = 0; q < nq; ++q) {
+          const float a = __shfl_sync(0xffffffffu, my_a, q);
+          const int sp = __shfl_sync(0xffffffffu, my_sp, q);
+          if (a == 0.f) continue;                            // warp-uniform
+          GateRows<J> R0;
+          load_rows<J>(R0, Pm, Hs, sp, true, Mc, ldh, Hq, ub, lane);
+          add_rows<J>(A, a, R0);
+        }
       }
-    }
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int u = ub + 4 * lane + 128 * j;
-      if (u >= Hq) continue;
-      const float4 gr = ldcg4(gi + u), gz = ldcg4(gi + Hq + u), gn = ldcg4(gi + 2 * Hq + u);
-      const float4 br = __ldg(reinterpret_cast<const float4*>(Lp.bias + u));
-      const float4 bz = __ldg(reinterpret_cast<const float4*>(Lp.bias + HP + u));
-      const float4 bi = __ldg(reinterpret_cast<const float4*>(Lp.bias + 2 * HP + u));
-      const float4 bh = __ldg(reinterpret_cast<const float4*>(Lp.bias + 3 * HP + u));
-      const float4 wk = __ldg(reinterpret_cast<const float4*>(Lp.wk + u));
-      float4 o;
-#define DAGNN_GATE(c)                                                          \
-  {                                                                            \
-    const float rg = fast_sigmoid(gr.c + ar[j].c + br.c);                      \
-    const float zg = fast_sigmoid(gz.c + az[j].c + bz.c);                      \
-    const float ng = fast_tanh(gn.c + bi.c + rg * (an[j].c + bh.c));           \
-    o.c = ng + zg * (am[j].c - ng);                                            \
-  }
-      DAGNN_GATE(x) DAGNN_GATE(y) DAGNN_GATE(z) DAGNN_GATE(w)
-#undef DAGNN_GATE
-      *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * ldh + u) = o;
-      skacc += o.x * wk.x + o.y * wk.y + o.z * wk.z + o.w * wk.w;       // units >= H: zero weights and biases -> o = 0
+      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
     }
   }
   skacc = warp_sum(skacc);
   if (lane == 0) Lp.sk[p] = skacc;
+  return true;
+}
+
+// the whole CTA (kBuilderWarps warps), one node with a long in-edge list: every warp derives the softmax statistics
+// (redundantly, in parallel), aggregates every kBuilderWarps-th in-edge, the partial sums meet in shared memory and
+// warp 0 finishes the node. `part` = [kBuilderWarps][4][128 J] floats of shared memory.
+template <int J>
+__device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, float* part, int warp,
+                                              int lane) {
+  const int Hq = P.Hq, Mc = P.Mc;
+  const long long ldh = P.ldh;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool use_ea = P.use_ea && D.eattr != nullptr;
+  const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
+  const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
+  float sum = 0.f, mx = -INFINITY;
+  for (int eb = e0; eb < e1; eb += 32) {
+    const int e = eb + lane;
+    int sp;
+    const float sc = (e < e1) ? edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, sp) : -INFINITY;
+    const float mnew = fmaxf(mx, warp_max(sc));
+    sum = sum * expf(mx - mnew) + warp_sum((e < e1) ? expf(sc - mnew) : 0.f);
+    mx = mnew;
+  }
+  const float inv = 1.f / (sum + 1e-16f);
+  float skacc = 0.f;
+#pragma unroll 1
+  for (int ub = 0; ub < Hq; ub += 128 * J) {
+    GateAcc A[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { A[j].r = z4; A[j].z = z4; A[j].n = z4; A[j].m = z4; }
+    // this warp's in-edges: e0 + warp + kBuilderWarps * t, one lane per t
+    for (int eb = e0 + warp; eb < e1; eb += 32 * kBuilderWarps) {
+      const int e = eb + kBuilderWarps * lane;
+      int my_sp = 0;
+      float my_a = 0.f;
+      if (e < e1) {
+        const float sc = edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, my_sp);
+        my_a = (my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
+      }
+      const int nq = min(32, (e1 - eb + kBuilderWarps - 1) / kBuilderWarps);
+      if constexpr (J <= 2) {
+        for (int q = 0; q < nq; q += 2) {
+          const float a0 = __shfl_sync(0xffffffffu, my_a, q), a1 = __shfl_sync(0xffffffffu, my_a, (q + 1) & 31);
+          const int s0 = __shfl_sync(0xffffffffu, my_sp, q), s1 = __shfl_sync(0xffffffffu, my_sp, (q + 1) & 31);
+          GateRows<J> R0, R1;
+          load_rows<J>(R0, Lp.Pm, Lp.Hs, s0, a0 != 0.f, Mc, ldh, Hq, ub, lane);
+          load_rows<J>(R1, Lp.Pm, Lp.Hs, s1, a1 != 0.f && q + 1 < nq, Mc, ldh, Hq, ub, lane);
+          add_rows<J>(A, a0, R0);
+          add_rows<J>(A, (q + 1 < nq) ? a1 : 0.f, R1);
+        }
+      } else {
+        for (int q = 0; q < nq; ++q) {
+          const float a0 = __shfl_sync(0xffffffffu, my_a, q);
+          const int s0 = __shfl_sync(0xffffffffu, my_sp, q);
+          if (a0 == 0.f) continue;
+          GateRows<J> R0;
+          load_rows<J>(R0, Lp.Pm, Lp.Hs, s0, true, Mc, ldh, Hq, ub, lane);
+          add_rows<J>(A, a0, R0);
+        }
+      }
+    }
+    float4* mine = reinterpret_cast<float4*>(part) + (size_t)warp * 4 * 32 * J;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      mine[(0 * J + j) * 32 + lane] = A[j].r; mine[(1 * J + j) * 32 + lane] = A[j].z;
+      mine[(2 * J + j) * 32 + lane] = A[j].n; mine[(3 * J + j) * 32 + lane] = A[j].m;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+    if (warp == 0) {
+      for (int w = 1; w < kBuilderWarps; ++w) {
+        const float4* o = reinterpret_cast<const float4*>(part) + (size_t)w * 4 * 32 * J;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const float4 r = o[(0 * J + j) * 32 + lane], z = o[(1 * J + j) * 32 + lane], n = o[(2 * J + j) * 32 + lane],
+                       m = o[(3 * J + j) * 32 + lane];
+          A[j].r.x += r.x; A[j].r.y += r.y; A[j].r.z += r.z; A[j].r.w += r.w;
+          A[j].z.x += z.x; A[j].z.y += z.y; A[j].z.z += z.z; A[j].z.w += z.w;
+          A[j].n.x += n.x; A[j].n.y += n.y; A[j].n.z += n.z; A[j].n.w += n.w;
+          A[j].m.x += m.x; A[j].m.y += m.y; A[j].m.z += m.z; A[j].m.w += m.w;
+        }
+      }
+      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+  }
+  if (warp == 0) {
+    skacc = warp_sum(skacc);
+    if (lane == 0) Lp.sk[p] = skacc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -581,6 +758,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
       // ---------------- gate phase of step s ----------------
       const int W = G * kBuilderWarps;
       if (warp < kBuilderWarps) {
+        if (tid == 0) S.ncoop = 0;
+        builders_sync();
         int rbase = 0;
         for (int q = 0; q < nseg; ++q) {
           const int d = q / P.layers, i = q - d * P.layers, l = s - i;
@@ -590,10 +769,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           // rows of the step are dealt to the warps of the grid, CTA-minor, continuing across segments
           int r = ((warp * G + rank) - rbase % W + W) % W;
           for (; r < n; r += W) {
-            if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane);
-            else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane);
+            bool done;
+            if (P.Hq <= 256) done = gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane, true);
+            else done = gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane, true);
+            if (!done) {                                  // long in-edge list: leave it to the whole CTA (or do it alone if full)
+              int slot = 0;
+              if (lane == 0) slot = atomicAdd(&S.ncoop, 1);
+              slot = __shfl_sync(0xffffffffu, slot, 0);
+              if (slot < kMaxCoop) {
+                if (lane == 0) { S.coop[slot][0] = q; S.coop[slot][1] = pos0 + r; }
+              } else if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, false, lane, false);
+              else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, false, lane, false);
+            }
           }
           rbase += n;
+        }
+        builders_sync();
+        const int nc = min(S.ncoop, kMaxCoop);
+        for (int c = 0; c < nc; ++c) {
+          const int q = S.coop[c][0], p = S.coop[c][1];
+          const int d = q / P.layers, i = q - d * P.layers;
+          const int pos0 = P.dir[d].lvl_off[s - i];
+          if (P.Hq <= 256) gate_row_coop<2>(P, P.dir[d], P.lay[d][i], p, pos0, reinterpret_cast<float*>(As), warp, lane);
+          else gate_row_coop<4>(P, P.dir[d], P.lay[d][i], p, pos0, reinterpret_cast<float*>(As), warp, lane);
         }
       }
       if (tr && tid == 0) tr[8] = clock64();
