@@ -73,7 +73,7 @@ EXPORTS = {
     "dagnn_schedule_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DagnnSchedule), vp, C.c_size_t, vp]),
     "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),
     "dagnn_pack_params_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.POINTER(DagnnPackLayout), vp, vp]),
-    "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
+    "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
     "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
     "dagnn_tc_selftest_f32": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),

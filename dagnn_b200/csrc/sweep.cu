@@ -58,13 +58,14 @@ struct LayP {
   const float* wk;      // [HP]
   const float* attnc;   // [4]
   const float* vidk;    // [nvid]
+  unsigned char* aimg;  // operand image of H[d][i]: fp16 hi/lo tiles in tcgen05 layout, written by the gate phase
   const __half* imgh;   // [W_hh^i ; W_ih^{i+1}] image (pack.cu)
   const __half* imgx;   // W_ih^0 image (layer 0 only)
 };
 struct SweepP {
   int dirs, layers, H, Hq, Mc, HP, nvid, use_ea;
   int Din0, nckx, nckh;       // layer-0 input width, 64-k chunks of the layer-0 input / of a state operand
-  int vec_x, N;
+  int vec_x, N, Kh64;
   long long ldh, ldx;
   const float* X;             // [N, ldx] node order (rows through perm)
   const int* summary;         // [0] number of levels of direction 0, [2] schedule status
@@ -198,15 +199,28 @@ __device__ __forceinline__ float edge_score(const SweepP& P, const DirP& D, cons
 }
 
 // GRU pointwise for the lane's units of one column pass; returns the lane's part of wk . h
+// The new state row is stored twice: fp32 (successors' gathers, readout) and as fp16 hi / lo halves straight into the
+// operand image of the projection GEMM (level-aligned 128-row tiles x 64-k chunks in the swizzled tcgen05 layout), so
+// that the GEMM's operand side is a plain bulk copy.
 template <int J>
-__device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, int p, int ub, int lane, const GateAcc (&A)[J]) {
+__device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, int p, int pos0, int lvl, int ub, int lane,
+                                             const GateAcc (&A)[J]) {
   const int Hq = P.Hq, HP = P.HP;
   const float* __restrict__ gi = Lp.Gi + (size_t)p * P.Mc;
+  const int rel = p - pos0;
+  unsigned char* itile = Lp.aimg + (size_t)((pos0 >> 7) + lvl + (rel >> 7)) * P.nckh * kAStageBytes;
+  const int rin = rel & 127;
   float skacc = 0.f;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int u = ub + 4 * lane + 128 * j;
-    if (u >= Hq) continue;
+    if (u >= P.Kh64) continue;
+    unsigned char* ihi = itile + (size_t)(u >> 6) * kAStageBytes + tc::tile_off(rin, (u & 63) >> 3) + (u & 4) * 2;
+    if (u >= Hq) {                                      // k padding of the last chunk: zeros (NaN bit patterns x 0 would poison the GEMM)
+      *reinterpret_cast<uint2*>(ihi) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) = make_uint2(0u, 0u);
+      continue;
+    }
     const float4 gr = ldcg4(gi + u), gz = ldcg4(gi + Hq + u), gn = ldcg4(gi + 2 * Hq + u);
     const float4 br = __ldg(reinterpret_cast<const float4*>(Lp.bias + u));
     const float4 bz = __ldg(reinterpret_cast<const float4*>(Lp.bias + HP + u));
@@ -224,6 +238,14 @@ __device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, in
     DAGNN_GATE(x) DAGNN_GATE(y) DAGNN_GATE(z) DAGNN_GATE(w)
 #undef DAGNN_GATE
     *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = o;
+    {
+      const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2half2_rn(o.z - f1.x, o.w - f1.y);
+      *reinterpret_cast<uint2*>(ihi) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
     skacc += o.x * wk.x + o.y * wk.y + o.z * wk.z + o.w * wk.w;       // units >= H: zero weights and biases -> o = 0
   }
   return skacc;
@@ -231,8 +253,9 @@ __device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, in
 
 // one warp, one node. Returns false (and does nothing) if the node has more than kCoopEdges in-edges and `may_defer`.
 template <int J>
-__device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, bool level0, int lane,
+__device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, int lane,
                                          bool may_defer) {
+  const bool level0 = lvl == 0;
   const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
   const float* __restrict__ Pm = Lp.Pm;
@@ -291,7 +314,7 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
           }
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
     }
   } else {
     // ---- long edge lists (a warp alone): softmax statistics first, 32 in-edges per round, then the weighted rows
@@ -328,7 +351,7 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
           add_rows<J>(A, a, R0);
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
     }
   }
   skacc = warp_sum(skacc);
@@ -340,8 +363,8 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
 // (redundantly, in parallel), aggregates every kBuilderWarps-th in-edge, the partial sums meet in shared memory and
 // warp 0 finishes the node. `part` = [kBuilderWarps][4][128 J] floats of shared memory.
 template <int J>
-__device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, float* part, int warp,
-                                              int lane) {
+__device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, float* part,
+                                              int warp, int lane) {
   const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -415,7 +438,7 @@ __device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, co
           A[j].m.x += m.x; A[j].m.y += m.y; A[j].m.z += m.z; A[j].m.w += m.w;
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, ub, lane, A);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   }
@@ -435,6 +458,7 @@ struct Tile {                 // one projection work item, identical in every th
   const __half* img;          // weight image of the source
   float* out0;                // columns [0, Mc)
   float* out1;                // columns [Mc, 2 Mc) or nullptr
+  const unsigned char* aimg;  // non-null: operand tiles come ready-made from this image (first 128-row tile of the work item)
   int K, nck, vec;            // valid operand width, 64-k chunks, rows are float4-loadable
   int p0, nrows, nst, cb0, ncb;   // first position, rows, 128-row sub-tiles, first 64-column block, blocks in this tile
 };
@@ -483,9 +507,9 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
   };
 
   Pre R;
-  prefetch(0, R);
+  if (!T.aimg) prefetch(0, R);
 #pragma unroll 1
-  for (int it = 0; it < nitems; ++it) {
+  for (int it = 0; it < (T.aimg ? 0 : nitems); ++it) {
     const int st = it % T.nst;
     const uint32_t j = ja + (uint32_t)it;
     const uint32_t stage = j % kNAS, use = j / kNAS;
@@ -506,8 +530,8 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
     for (int q = 0; q < kNR; ++q)                                      // rows beyond the tile: D rows nobody reads
       if (q < nx && ra + kRStride * q < T.nrows) tc::store_split8(A_hi, A_lo, r0 + kRStride * q, c8, x[q]);
     tc::fence_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&S.a_full[stage]);
+    builders_sync();
+    if (tid == 0) mbar_arrive(&S.a_full[stage]);
   }
   if (trc) tr[1] = clock64();
 
@@ -596,6 +620,23 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   const int npre = min(nbs, T.nck);
   for (int c = (int)R.pre; c < npre; ++c) ring_load(T, nbc, c, Bs, S, R);
   R.pre = 0;
+  // operand side when the tiles come ready-made: item it = (chunk c, sub-tile st) -> stage (ja + it) % kNAS, two bulk copies
+  // (hi, lo) of the rows the sub-tile really has, rounded up to the 8-row swizzle group
+  const int nitems = T.nck * T.nst;
+  auto load_A = [&](int it) {
+    const int c = it / T.nst, st = it - c * T.nst;
+    const uint32_t j = ja + (uint32_t)it;
+    const uint32_t stage = j % kNAS, use = j / kNAS;
+    if (use >= 1) mbar_wait(&S.a_empty[stage], (use - 1) & 1u);        // MMAs that read this stage are done
+    const uint32_t bytes = (uint32_t)((min(128, T.nrows - st * 128) + 7) & ~7) * tc::ROW_BYTES;
+    const unsigned char* src = T.aimg + ((size_t)st * T.nck + c) * kAStageBytes;
+    unsigned char* dst = As + (size_t)stage * kAStageBytes;
+    mbar_expect_tx(&S.a_full[stage], 2 * bytes);
+    bulk_g2s(dst, src, bytes, &S.a_full[stage]);
+    bulk_g2s(dst + 128 * tc::ROW_BYTES, src + 128 * tc::ROW_BYTES, bytes, &S.a_full[stage]);
+  };
+  if (T.aimg)
+    for (int it = 0; it < min(kNAS, nitems); ++it) load_A(it);
 #pragma unroll 1
   for (int c = 0; c < T.nck; ++c) {
     const uint32_t s = (first + (uint32_t)c) % (uint32_t)nbs;
@@ -615,6 +656,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
       tc::commit(&S.a_empty[stage]);
+      if (T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
     }
     tc::commit(&S.b_empty[s]);
     R.pending |= 1u << s;
@@ -665,7 +707,7 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   Tile T;
   if (s < 0) {
     const int d = it.q;
-    T.A = P.X; T.lda = P.ldx; T.perm = P.dir[d].perm; T.img = P.lay[d][0].imgx;
+    T.A = P.X; T.lda = P.ldx; T.perm = P.dir[d].perm; T.img = P.lay[d][0].imgx; T.aimg = nullptr;
     T.out0 = P.lay[d][0].Gi; T.out1 = nullptr;
     T.K = P.Din0; T.nck = P.nckx; T.vec = P.vec_x;
   } else {
@@ -677,6 +719,10 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   }
   T.p0 = g.pos0 + rt * rows_per;
   T.nrows = min(rows_per, g.n - rt * rows_per);
+  if (s >= 0) {
+    const int d = it.q / P.layers, i = it.q - d * P.layers;
+    T.aimg = P.lay[d][i].aimg + (size_t)((g.pos0 >> 7) + (s - i) + rt * tb.nst) * P.nckh * kAStageBytes;
+  }
   T.nst = (T.nrows + 127) >> 7;
   T.cb0 = ctile * tb.nbc;
   T.ncb = min(tb.nbc, nblk - T.cb0);
@@ -727,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   SmemTail& S = *reinterpret_cast<SmemTail*>(Bs + kBRegionBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < kNAS; ++s) { mbar_init(&S.a_full[s], kBuilderWarps); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < kNAS; ++s) { mbar_init(&S.a_full[s], 1); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < kNBBar; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     mbar_init(&S.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -770,16 +816,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           int r = ((warp * G + rank) - rbase % W + W) % W;
           for (; r < n; r += W) {
             bool done;
-            if (P.Hq <= 256) done = gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane, true);
-            else done = gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l == 0, lane, true);
+            if (P.Hq <= 256) done = gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, true);
+            else done = gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, true);
             if (!done) {                                  // long in-edge list: leave it to the whole CTA (or do it alone if full)
               int slot = 0;
               if (lane == 0) slot = atomicAdd(&S.ncoop, 1);
               slot = __shfl_sync(0xffffffffu, slot, 0);
               if (slot < kMaxCoop) {
                 if (lane == 0) { S.coop[slot][0] = q; S.coop[slot][1] = pos0 + r; }
-              } else if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, false, lane, false);
-              else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, false, lane, false);
+              } else if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, false);
+              else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, false);
             }
           }
           rbase += n;
@@ -790,8 +836,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           const int q = S.coop[c][0], p = S.coop[c][1];
           const int d = q / P.layers, i = q - d * P.layers;
           const int pos0 = P.dir[d].lvl_off[s - i];
-          if (P.Hq <= 256) gate_row_coop<2>(P, P.dir[d], P.lay[d][i], p, pos0, reinterpret_cast<float*>(As), warp, lane);
-          else gate_row_coop<4>(P, P.dir[d], P.lay[d][i], p, pos0, reinterpret_cast<float*>(As), warp, lane);
+          if (P.Hq <= 256) gate_row_coop<2>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
+          else gate_row_coop<4>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
         }
       }
       if (tr && tid == 0) tr[8] = clock64();
@@ -847,11 +893,19 @@ using namespace dagnn;
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E) {
-  if (dirs < 1 || dirs > DAGNN_MAX_DIRS || layers < 1 || layers > DAGNN_MAX_LAYERS || Din < 1 || H < 1 || N < 0 || E < 0) return 0;
+// operand image of one (direction, layer): 128-row tiles aligned to level starts — tile index of position p in level l
+// (first position pos0) = pos0 / 128 + l + (p - pos0) / 128 — times the 64-k chunks of H, 32 KB (hi + lo) each
+static size_t aimg_bytes(int H, int64_t N, int max_levels) {
+  return align256((size_t)((N >> 7) + max_levels + 2) * (size_t)(round_up(H, 64) / 64) * kAStageBytes);
+}
+extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E,
+                                              int32_t max_levels) {
+  if (dirs < 1 || dirs > DAGNN_MAX_DIRS || layers < 1 || layers > DAGNN_MAX_LAYERS || Din < 1 || H < 1 || N < 0 || E < 0 || max_levels < 1)
+    return 0;
   const size_t Mc = (size_t)round_up(3 * round_up(H, 4), 64);
-  // per (direction, layer): key scores [N], hidden projection P [N, Mc], input projection Gi [N, Mc]
-  return 256 + (size_t)dirs * layers * (align256((size_t)N * sizeof(float)) + 2 * align256((size_t)N * Mc * sizeof(float)));
+  // per (direction, layer): key scores [N], hidden projection P [N, Mc], input projection Gi [N, Mc], operand image of H
+  return 256 + (size_t)dirs * layers * (align256((size_t)N * sizeof(float)) + 2 * align256((size_t)N * Mc * sizeof(float)) +
+                                        aimg_bytes(H, N, max_levels));
 }
 extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)(max_steps + 1) * 256 * 16 * sizeof(long long); }
 
@@ -865,7 +919,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   DAGNN_REQUIRE(A->X && A->ldx >= A->Din && A->Din > 0, "sweep: X");
   DAGNN_REQUIRE(A->ldh % 4 == 0 && A->ldh >= round_up(H, 4), "sweep: ldh must be a multiple of 4 and >= roundup(H,4)");
   DAGNN_REQUIRE(A->workspace && ((uintptr_t)A->workspace & 255) == 0, "sweep: workspace must be 256-byte aligned");
-  if (A->workspace_bytes < dagnn_sweep_workspace_bytes(dirs, layers, A->Din, H, S->N, S->E))
+  if (A->workspace_bytes < dagnn_sweep_workspace_bytes(dirs, layers, A->Din, H, S->N, S->E, S->max_levels))
     return set_err(DAGNN_E_WORKSPACE, "sweep: workspace too small (dagnn_sweep_workspace_bytes)");
   if (H < 1 || H > 4096) return set_err(DAGNN_E_UNSUPPORTED, "sweep: hidden size %d not in [1,4096]", H);
   if (A->nvid < 0) return set_err(DAGNN_E_INVALID, "sweep: nvid");
@@ -878,7 +932,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   P.dirs = dirs; P.layers = layers; P.H = H; P.Hq = lay[0].Hq; P.Mc = lay[0].Mc; P.HP = lay[0].HP; P.nvid = A->nvid;
   P.use_ea = A->use_edge_attr; P.Din0 = A->Din; P.nckx = lay[0].Kin64 / 64; P.nckh = lay[0].Kh64 / 64;
   P.vec_x = ((A->ldx & 3) == 0 && (A->Din & 3) == 0 && ((uintptr_t)A->X & 15) == 0) ? 1 : 0;
-  P.N = (int)S->N;
+  P.N = (int)S->N; P.Kh64 = lay[0].Kh64;
   P.ldh = A->ldh; P.ldx = A->ldx; P.X = A->X; P.summary = S->summary; P.bar = static_cast<unsigned int*>(A->workspace);
   P.trace = static_cast<long long*>(A->trace);
   char* ws = static_cast<char*>(A->workspace) + 256;
@@ -900,6 +954,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
       q.sk = reinterpret_cast<float*>(ws); ws += sk_bytes;
       q.Pm = reinterpret_cast<float*>(ws); ws += pm_bytes;
       q.Gi = reinterpret_cast<float*>(ws); ws += pm_bytes;
+      q.aimg = reinterpret_cast<unsigned char*>(ws); ws += aimg_bytes(H, S->N, S->max_levels);
     }
   }
 

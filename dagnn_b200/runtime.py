@@ -250,8 +250,8 @@ class PackedParams(object):
 _WS = {}
 
 
-def _sweep_workspace(device, dirs, layers, Din, H, N, E) -> torch.Tensor:
-    need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H, N, E))
+def _sweep_workspace(device, dirs, layers, Din, H, N, E, max_levels) -> torch.Tensor:
+    need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H, N, E, max_levels))
     key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     w = _WS.get(key)
     if w is None or w.numel() * 4 < need:
@@ -268,7 +268,7 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
     dirs, N = sched.c.dirs, sched.c.N
     ldh = (H + 3) // 4 * 4
     Hs = torch.empty(dirs, num_layers, N, ldh, device=X.device, dtype=torch.float32)
-    ws = _sweep_workspace(X.device, dirs, num_layers, Din, H, N, sched.c.E)
+    ws = _sweep_workspace(X.device, dirs, num_layers, Din, H, N, sched.c.E, sched.c.max_levels)
     a = DagnnSweepArgs()
     a.sched = C.pointer(sched.c)
     for d in range(dirs):

@@ -163,7 +163,7 @@ typedef struct DagnnSweepArgs {
                                           issuer: 12 waiting for weights, 13 waiting for operands, 14 issuing, 15 #stages  */
 } DagnnSweepArgs;
 
-size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E);
+size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E, int32_t max_levels);
 size_t dagnn_sweep_trace_bytes(int32_t max_steps);
 int dagnn_sweep_forward_f32(const DagnnSweepArgs* args, void* stream);
 

@@ -41,9 +41,9 @@ def test_pack_layout_and_workspace_queries(built_lib):
     assert (L.Hq, L.Mc, L.Kin64, L.Kh64, L.HP) == (504, 1536, 64, 512, 512)
     assert built_lib.dagnn_pack_layout(0, 16, 0, 1, 1, C.byref(L)) != 0         # bad argument -> error code + message
     assert b"pack_layout" in built_lib.dagnn_last_error()
-    ws = built_lib.dagnn_sweep_workspace_bytes(2, 2, 256, 256, 16478, 24491)
+    ws = built_lib.dagnn_sweep_workspace_bytes(2, 2, 256, 256, 16478, 24491, 256)
     assert ws >= 256 + 4 * (16478 * 4 + 2 * 16478 * 768 * 4)
-    assert built_lib.dagnn_sweep_workspace_bytes(3, 2, 256, 256, 10, 10) == 0   # dirs out of range
+    assert built_lib.dagnn_sweep_workspace_bytes(3, 2, 256, 256, 10, 10, 256) == 0   # dirs out of range
     assert built_lib.dagnn_schedule_workspace_bytes(1000, 2000, 256) > 0
     assert built_lib.dagnn_sweep_trace_bytes(10) == 11 * 256 * 16 * 8
 
