@@ -38,6 +38,7 @@ constexpr int kBRegionBytes = 8 * kBlkBytes;             // weight ring: 2 x 4 b
 constexpr int kNBBar = 8;
 constexpr int kMaxSeg = DAGNN_MAX_DIRS * DAGNN_MAX_LAYERS;
 constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 columns
+constexpr int kMaxChunks = 16;                           // k chunks of a tile that may use compact operand stages
 constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (8 warps split the edge list)
 constexpr int kMaxCoop = 48;       // ... per CTA and gate phase; beyond that a warp does the node alone
 constexpr int kMaxSmem = 232448;                         // 227 KB opt-in limit per CTA on sm_100
@@ -87,6 +88,7 @@ struct SmemTail {
   int coop[kMaxCoop][2];      // gate phase: (segment, position) of the nodes this CTA aggregates cooperatively
   int ncoop;
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
+  uint64_t c_full[kMaxChunks];      // small tiles: operand chunk c has landed
   uint32_t tmem_slot;
 };
 constexpr size_t kSmemBytes = 1024 + (size_t)kNAS * kAStageBytes + kBRegionBytes + sizeof(SmemTail);
@@ -461,7 +463,12 @@ struct Tile {                 // one projection work item, identical in every th
   const unsigned char* aimg;  // non-null: operand tiles come ready-made from this image (first 128-row tile of the work item)
   int K, nck, vec;            // valid operand width, 64-k chunks, rows are float4-loadable
   int p0, nrows, nst, cb0, ncb;   // first position, rows, 128-row sub-tiles, first 64-column block, blocks in this tile
+  int small;                  // > 0: compact operand stages of `small` rows, every k chunk has its own stage (tail levels)
 };
+// Tail levels hold a handful of rows per tile. When all k chunks of such a tile fit into the operand region at once
+// (stage = hi + lo tile of roundup(rows, 8) rows), nothing waits for a free stage: every operand chunk is in flight at
+// once and the MMAs of a chunk start as soon as it has landed. The MMA still reads 128 rows from the stage base: the
+// rows behind the stage are other stages' bytes — D rows nobody reads.
 
 // raw operands of one work item of a builder thread, loaded one item ahead: kNR rows (r0 + x * kRStride of the sub-tile),
 // 8 consecutive k
@@ -610,7 +617,7 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
 }
 
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
-                                            uint32_t ja, RingState& R, const Tile* nextT, int next_nbc) {
+                                            uint32_t ja, uint32_t cs, RingState& R, const Tile* nextT, int next_nbc) {
   const int nbs = 8 / nbc;
   const uint32_t idesc = tc::instr_desc_f16(128, 64 * T.ncb);
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
@@ -635,8 +642,18 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
     bulk_g2s(dst, src, bytes, &S.a_full[stage]);
     bulk_g2s(dst + 128 * tc::ROW_BYTES, src + 128 * tc::ROW_BYTES, bytes, &S.a_full[stage]);
   };
-  if (T.aimg)
+  const uint32_t sbytes = 2u * (uint32_t)T.small * tc::ROW_BYTES;      // compact stage: hi + lo tile of T.small rows
+  if (T.small) {
+    for (int c = 0; c < T.nck; ++c) {
+      const unsigned char* src = T.aimg + (size_t)c * kAStageBytes;
+      unsigned char* dst = As + (size_t)c * sbytes;
+      mbar_expect_tx(&S.c_full[c], sbytes);
+      bulk_g2s(dst, src, sbytes / 2, &S.c_full[c]);
+      bulk_g2s(dst + sbytes / 2, src + 128 * tc::ROW_BYTES, sbytes / 2, &S.c_full[c]);
+    }
+  } else if (T.aimg) {
     for (int it = 0; it < min(kNAS, nitems); ++it) load_A(it);
+  }
 #pragma unroll 1
   for (int c = 0; c < T.nck; ++c) {
     const uint32_t s = (first + (uint32_t)c) % (uint32_t)nbs;
@@ -648,15 +665,18 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
     for (int st = 0; st < T.nst; ++st) {
       const uint32_t j = ja + (uint32_t)(c * T.nst + st);
       const uint32_t stage = j % kNAS, use = j / kNAS;
-      mbar_wait(&S.a_full[stage], use & 1u);
+      if (T.small) mbar_wait(&S.c_full[c], cs >> c & 1u);
+      else mbar_wait(&S.a_full[stage], use & 1u);
       tc::fence_after_sync();
-      const uint32_t sa = smem_u32(As + (size_t)stage * kAStageBytes);
-      const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + 128 * tc::ROW_BYTES);
+      const uint32_t sa = T.small ? smem_u32(As + (size_t)c * sbytes) : smem_u32(As + (size_t)stage * kAStageBytes);
+      const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + (T.small ? sbytes / 2 : 128 * tc::ROW_BYTES));
       const uint32_t tm = tmem + (uint32_t)(st * 64 * nbc);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
-      tc::commit(&S.a_empty[stage]);
-      if (T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
+      if (!T.small) {
+        tc::commit(&S.a_empty[stage]);
+        if (T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
+      }
     }
     tc::commit(&S.b_empty[s]);
     R.pending |= 1u << s;
@@ -723,14 +743,19 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
     const int d = it.q / P.layers, i = it.q - d * P.layers;
     T.aimg = P.lay[d][i].aimg + (size_t)((g.pos0 >> 7) + (s - i) + rt * tb.nst) * P.nckh * kAStageBytes;
   }
+  T.small = 0;
+  if (T.aimg && T.nst == 1 && T.nck <= kMaxChunks) {
+    const int rp8 = (T.nrows + 7) & ~7;
+    if (T.nck * 2 * rp8 * tc::ROW_BYTES <= kNAS * kAStageBytes) T.small = rp8;
+  }
   T.nst = (T.nrows + 127) >> 7;
   T.cb0 = ctile * tb.nbc;
   T.ncb = min(tb.nbc, nblk - T.cb0);
   return T;
 }
-// all threads; two __syncthreads inside
+// one warp (lanes = segments); the caller publishes the table with a CTA-wide barrier
 __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg_max, int G) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x & 31;
   const int nseg = (s < 0) ? P.dirs : nseg_max;
   if (tid < kMaxSeg) {
     Seg g = {0, 0, 0, 0};
@@ -748,7 +773,7 @@ __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, i
     }
     tb.seg[tid] = g;
   }
-  __syncthreads();
+  __syncwarp();
   if (tid == 0) {
     int t64 = 0;                                        // work in units of 128 rows x 64 columns
     for (int q = 0; q < nseg; ++q) t64 += ceil_div(tb.seg[q].n, 128) * seg_blocks(P, s, q);
@@ -762,7 +787,7 @@ __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, i
     }
     tb.nbc = nbc; tb.nst = nst;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ SweepP P) {
@@ -775,6 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   if (tid == 0) {
     for (int s = 0; s < kNAS; ++s) { mbar_init(&S.a_full[s], 1); mbar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < kNBBar; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
+    for (int s = 0; s < kMaxChunks; ++s) mbar_init(&S.c_full[s], 1);
     mbar_init(&S.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -790,10 +816,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   const int nsteps = ok ? L + P.layers - 1 : 0;
   const int nseg = P.dirs * P.layers;
   const int G = (int)gridDim.x, rank = (int)blockIdx.x;
-  uint32_t ja = 0, ct = 0;                     // operand-ring items and tiles processed so far (mbarrier phases)
+  uint32_t ja = 0, ct = 0, cs = 0;             // operand-ring items and tiles processed so far, phase bits of the chunk barriers
   RingState R = {0u, 0u, 0u, 0u, 0u, 0u, 0};
   unsigned int nbar = 0;
-  if (nsteps > 0) build_step_table(P, S.tab[1], -1, L, nseg, G);      // proj phase s uses tab[s & 1]; -1 & 1 == 1
+  // proj phase s uses tab[s & 1] (-1 & 1 == 1). Level offsets are constants: the issuer warp builds the table of phase
+  // s + 1 while the builder warps run the gate phase of step s, the grid barrier after it publishes the table.
+  if (nsteps > 0 && warp == kBuilderWarps) {
+    build_step_table(P, S.tab[1], -1, L, nseg, G);
+    build_step_table(P, S.tab[0], 0, L, nseg, G);
+  }
+  __syncthreads();
 
   // gate phase of step s (s >= 0), then proj phase s (s = -1: X)
 #pragma unroll 1
@@ -840,6 +872,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           else gate_row_coop<4>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
         }
       }
+      else if (s + 1 < nsteps) build_step_table(P, S.tab[(s + 1) & 1], s + 1, L, nseg, G);
       if (tr && tid == 0) tr[8] = clock64();
       if (s + 1 < nsteps) grid_barrier(P.bar, ++nbar * (unsigned int)G);   // the last step's projection is empty
       if (tr && tid == 0) tr[9] = clock64();
@@ -850,7 +883,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
     const StepTab& tb = S.tab[s & 1];
     StepTab& tbn = S.tab[(s + 1) & 1];
     const bool has_next = s + 1 < nsteps;
-    if (has_next) build_step_table(P, tbn, s + 1, L, nseg, G);
     const int nseg_now = (s < 0) ? P.dirs : nseg;
     int my_tiles = 0;
     TileIt it = {0, -1};
@@ -871,10 +903,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           hn = tile_advance(tbn, nseg, rank, G, it2);
           if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
         }
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, R, hn ? &N : nullptr, nn);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, R, hn ? &N : nullptr, nn);
       }
       __syncwarp();
-      ja += (uint32_t)(T.nck * T.nst);
+      if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier
+      else ja += (uint32_t)(T.nck * T.nst);
       ct += 1;
       ++my_tiles;
     }
