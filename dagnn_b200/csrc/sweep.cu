@@ -80,7 +80,8 @@ struct Seg {
   int pos0, n, ntile, base;
 };
 struct StepTab {
-  Seg seg[kMaxSeg];
+  Seg seg[kMaxSeg];           // projection of step s: rows to project (empty when nothing downstream needs them)
+  int gpos0[kMaxSeg], gn[kMaxSeg];   // gate phase of step s: first position and rows of every segment's level
   int nbc, nst;               // 64-column blocks per tile (1, 2, 4), 128-row sub-tiles per tile
 };
 struct SmemTail {
@@ -126,8 +127,10 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 // all CTAs of the (cooperative, co-resident) grid; `target` = arrivals expected so far
+// Only the builder warps write global memory, so they alone gate the arrival (named barrier 1); the issuer warp, which may
+// still be queueing weight prefetches, joins at the closing CTA-wide barrier.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
-  __syncthreads();
+  if (threadIdx.x < kBuilders) asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
@@ -205,10 +208,24 @@ __device__ __forceinline__ float edge_score(const SweepP& P, const DirP& D, cons
 // operand image of the projection GEMM (level-aligned 128-row tiles x 64-k chunks in the swizzled tcgen05 layout), so
 // that the GEMM's operand side is a plain bulk copy.
 template <int J>
-__device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, int p, int pos0, int lvl, int ub, int lane,
-                                             const GateAcc (&A)[J]) {
-  const int Hq = P.Hq, HP = P.HP;
+struct GiRow {                     // the node's own input projection, lane's units
+  float4 r[J], z[J], n[J];
+};
+template <int J>
+__device__ __forceinline__ void load_gi(GiRow<J>& Gr, const SweepP& P, const LayP& Lp, int p, int ub, int lane) {
   const float* __restrict__ gi = Lp.Gi + (size_t)p * P.Mc;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int u = ub + 4 * lane + 128 * j;
+    Gr.r[j] = z4; Gr.z[j] = z4; Gr.n[j] = z4;
+    if (u < P.Hq) { Gr.r[j] = ldcg4(gi + u); Gr.z[j] = ldcg4(gi + P.Hq + u); Gr.n[j] = ldcg4(gi + 2 * P.Hq + u); }
+  }
+}
+template <int J>
+__device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, int p, int pos0, int lvl, int ub, int lane,
+                                             const GateAcc (&A)[J], const GiRow<J>& Gr) {
+  const int Hq = P.Hq, HP = P.HP;
   const int rel = p - pos0;
   unsigned char* itile = Lp.aimg + (size_t)((pos0 >> 7) + lvl + (rel >> 7)) * P.nckh * kAStageBytes;
   const int rin = rel & 127;
@@ -223,7 +240,7 @@ __device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, in
       *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) = make_uint2(0u, 0u);
       continue;
     }
-    const float4 gr = ldcg4(gi + u), gz = ldcg4(gi + Hq + u), gn = ldcg4(gi + 2 * Hq + u);
+    const float4 gr = Gr.r[j], gz = Gr.z[j], gn = Gr.n[j];
     const float4 br = __ldg(reinterpret_cast<const float4*>(Lp.bias + u));
     const float4 bz = __ldg(reinterpret_cast<const float4*>(Lp.bias + HP + u));
     const float4 bi = __ldg(reinterpret_cast<const float4*>(Lp.bias + 2 * HP + u));
@@ -253,10 +270,9 @@ __device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, in
   return skacc;
 }
 
-// one warp, one node. Returns false (and does nothing) if the node has more than kCoopEdges in-edges and `may_defer`.
+// one warp, one node
 template <int J>
-__device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, int lane,
-                                         bool may_defer) {
+__device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, int lane) {
   const bool level0 = lvl == 0;
   const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
@@ -268,7 +284,6 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
   int e0 = 0, e1 = 0;
   if (!level0) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
   const int ne = e1 - e0;
-  if (may_defer && ne > kCoopEdges) return false;
   float skacc = 0.f;
   if (ne <= 32) {
     // ---- the common case: all in-edges in one round, one lane per edge
@@ -281,6 +296,8 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
       GateAcc A[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) { A[j].r = z4; A[j].z = z4; A[j].n = z4; A[j].m = z4; }
+      GiRow<J> Gr;
+      if constexpr (J <= 2) load_gi<J>(Gr, P, Lp, p, ub, lane);     // independent of the in-edges: in flight from the start
       if (ne > 0) {
         // rows of the first in-edges go in flight before the softmax (their address needs the edge list only)
         constexpr bool kTwo = J <= 2;                      // two in-edges in flight per lane when the registers allow it
@@ -316,7 +333,8 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
           }
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
+      if constexpr (J > 2) load_gi<J>(Gr, P, Lp, p, ub, lane);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A, Gr);
     }
   } else {
     // ---- long edge lists (a warp alone): softmax statistics first, 32 in-edges per round, then the weighted rows
@@ -353,19 +371,20 @@ __device__ __forceinline__ bool gate_row(const SweepP& P, const DirP& D, const L
           add_rows<J>(A, a, R0);
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
+      GiRow<J> Gr;
+      load_gi<J>(Gr, P, Lp, p, ub, lane);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A, Gr);
     }
   }
   skacc = warp_sum(skacc);
   if (lane == 0) Lp.sk[p] = skacc;
-  return true;
 }
 
 // the whole CTA (kBuilderWarps warps), one node with a long in-edge list: every warp derives the softmax statistics
 // (redundantly, in parallel), aggregates every kBuilderWarps-th in-edge, the partial sums meet in shared memory and
 // warp 0 finishes the node. `part` = [kBuilderWarps][4][128 J] floats of shared memory.
 template <int J>
-__device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, float* part,
+__device__ __noinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, float* part,
                                               int warp, int lane) {
   const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
@@ -440,7 +459,9 @@ __device__ __forceinline__ void gate_row_coop(const SweepP& P, const DirP& D, co
           A[j].m.x += m.x; A[j].m.y += m.y; A[j].m.z += m.z; A[j].m.w += m.w;
         }
       }
-      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A);
+      GiRow<J> Gr;
+      load_gi<J>(Gr, P, Lp, p, ub, lane);
+      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A, Gr);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   }
@@ -759,19 +780,21 @@ __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, i
   const int nseg = (s < 0) ? P.dirs : nseg_max;
   if (tid < kMaxSeg) {
     Seg g = {0, 0, 0, 0};
+    int gp = 0, gnn = 0;
     if (tid < nseg) {
       if (s < 0) g.n = P.N;
       else {
         const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
-        // the last level's states have no successors: only the next layer's input projection is still needed
-        const bool needed = (l >= 0 && l < L) && (l + 1 < L || i + 1 < P.layers);
-        if (needed) {
-          g.pos0 = P.dir[d].lvl_off[l];
-          g.n = max(0, P.dir[d].lvl_off[l + 1] - g.pos0);
+        if (l >= 0 && l < L) {
+          gp = P.dir[d].lvl_off[l];
+          gnn = max(0, P.dir[d].lvl_off[l + 1] - gp);
+          // the last level's states have no successors: only the next layer's input projection is still needed
+          if (l + 1 < L || i + 1 < P.layers) { g.pos0 = gp; g.n = gnn; }
         }
       }
     }
     tb.seg[tid] = g;
+    tb.gpos0[tid] = gp; tb.gn[tid] = gnn;
   }
   __syncwarp();
   if (tid == 0) {
@@ -790,6 +813,9 @@ __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, i
   __syncwarp();
 }
 
+// J = float4 column groups per lane in the gate phase: 2 covers H <= 256 in one pass, 4 wider states (one instantiation
+// each keeps the instruction footprint of a launch small — the kernel hops between phases ~130 times per forward)
+template <int J>
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ SweepP P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -841,24 +867,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
         int rbase = 0;
         for (int q = 0; q < nseg; ++q) {
           const int d = q / P.layers, i = q - d * P.layers, l = s - i;
-          if (l < 0 || l >= L) continue;
+          const int pos0 = S.tab[s & 1].gpos0[q], n = S.tab[s & 1].gn[q];     // level offsets: table built one phase ahead
+          if (n <= 0) continue;
           const DirP& D = P.dir[d];
-          const int pos0 = D.lvl_off[l], n = D.lvl_off[l + 1] - pos0;
           // rows of the step are dealt to the warps of the grid, CTA-minor, continuing across segments
           int r = ((warp * G + rank) - rbase % W + W) % W;
           for (; r < n; r += W) {
-            bool done;
-            if (P.Hq <= 256) done = gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, true);
-            else done = gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, true);
-            if (!done) {                                  // long in-edge list: leave it to the whole CTA (or do it alone if full)
+            const int p = pos0 + r;
+            if (l > 0 && D.rowptr[p + 1] - D.rowptr[p] > kCoopEdges) {     // long in-edge list: leave it to the whole CTA
               int slot = 0;
               if (lane == 0) slot = atomicAdd(&S.ncoop, 1);
               slot = __shfl_sync(0xffffffffu, slot, 0);
               if (slot < kMaxCoop) {
-                if (lane == 0) { S.coop[slot][0] = q; S.coop[slot][1] = pos0 + r; }
-              } else if (P.Hq <= 256) gate_row<2>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, false);
-              else gate_row<4>(P, D, P.lay[d][i], pos0 + r, pos0, l, lane, false);
+                if (lane == 0) { S.coop[slot][0] = q; S.coop[slot][1] = p; }
+                continue;
+              }
             }
+            gate_row<J>(P, D, P.lay[d][i], p, pos0, l, lane);
           }
           rbase += n;
         }
@@ -867,9 +892,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
         for (int c = 0; c < nc; ++c) {
           const int q = S.coop[c][0], p = S.coop[c][1];
           const int d = q / P.layers, i = q - d * P.layers;
-          const int pos0 = P.dir[d].lvl_off[s - i];
-          if (P.Hq <= 256) gate_row_coop<2>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
-          else gate_row_coop<4>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
+          const int pos0 = S.tab[s & 1].gpos0[q];
+          gate_row_coop<J>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
         }
       }
       else if (s + 1 < nsteps) build_step_table(P, S.tab[(s + 1) & 1], s + 1, L, nseg, G);
@@ -996,7 +1020,8 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   static int sm_count[64] = {0};
   if (dev >= 64) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device ordinal %d", dev);
   if (sm_count[dev] == 0) {
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     int n = 0, coop = 0;
     DAGNN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     DAGNN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1006,6 +1031,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   const int G = sm_count[dev];
   DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 16, st));
   void* kargs[] = {(void*)&P};
-  DAGNN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(G), dim3(kThreads), kargs, kSmemBytes, st));
+  const void* kern = P.Hq <= 256 ? (const void*)k_sweep<2> : (const void*)k_sweep<4>;
+  DAGNN_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(kThreads), kargs, kSmemBytes, st));
   return check_launch("k_sweep");
 }
