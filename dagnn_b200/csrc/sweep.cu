@@ -84,7 +84,9 @@ struct StepTab {
   int gpos0[kMaxSeg], gn[kMaxSeg];   // gate phase of step s: first position and rows of every segment's level
   int nbc, nst;               // 64-column blocks per tile (1, 2, 4), 128-row sub-tiles per tile
 };
+constexpr int kEpiLd = 20;    // floats per scratch row: 16 columns + pad (16-byte aligned rows)
 struct SmemTail {
+  float epi[kBuilderWarps][32 * kEpiLd];   // projection epilogue: 32 rows x 16 columns per warp, transposed for row-contiguous stores
   StepTab tab[2];             // this proj phase's and the next one's segment tables
   int coop[kMaxCoop][2];      // gate phase: (segment, position) of the nodes this CTA aggregates cooperatively
   int ncoop;
@@ -569,24 +571,38 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
   if (trc) tr[2] = clock64();
   {
     const int q = warp & 3, cg = warp >> 2;
-    const int ngrp = T.ncb * 8;                           // 8-column groups of the tile
+    const int ngrp = T.ncb * 2;                           // 32-column groups of the tile (a 64-column block = 2 groups)
     const int Mc = P.Mc;
 #pragma unroll 1
     for (int st = 0; st < T.nst; ++st) {
-      const int r = st * 128 + 32 * q + lane;            // TMEM lane = row inside the sub-tile
-      const bool rok = r < T.nrows;
-      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(st * tile_cols);
+      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(st * tile_cols);   // TMEM lane = row of the sub-tile
 #pragma unroll 1
       for (int g = cg; g < ngrp; g += kBuilderWarps / 4) {
-        float v[8];
+        float v[32];
         __syncwarp();
-        tc::ld8(tbase + (uint32_t)(8 * g), v);
+        tc::ld32(tbase + (uint32_t)(32 * g), v);
         tc::wait_ld();
-        if (rok) {
-          const int col = T.cb0 * 64 + 8 * g;
-          float* dst = (col < Mc) ? T.out0 + (size_t)(T.p0 + r) * Mc + col : T.out1 + (size_t)(T.p0 + r) * Mc + (col - Mc);
-          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        // TMEM hands every lane one ROW (32 columns); stored like that, a warp instruction would scatter 16-byte pieces
+        // over 32 rows (partial sectors). Transpose through shared memory: 8 lanes then write 128 contiguous bytes of a row.
+        float* sc = S.epi[warp];
+        const int col = T.cb0 * 64 + 32 * g;             // a 32-column group never straddles the two projected matrices
+        float* dst0 = (col < Mc) ? T.out0 + col : T.out1 + (col - Mc);
+        const int rbase = st * 128 + 32 * q;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                     // two halves of 16 columns
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(sc + lane * kEpiLd + 4 * k) =
+                make_float4(v[16 * h + 4 * k], v[16 * h + 4 * k + 1], v[16 * h + 4 * k + 2], v[16 * h + 4 * k + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = 8 * k + (lane >> 2);          // 8 rows per instruction, 4 lanes x 16 bytes each (two full sectors)
+            if (rbase + rr < T.nrows)
+              *reinterpret_cast<float4*>(dst0 + (size_t)(T.p0 + rbase + rr) * Mc + 16 * h + 4 * (lane & 3)) =
+                  *reinterpret_cast<const float4*>(sc + rr * kEpiLd + 4 * (lane & 3));
+          }
+          __syncwarp();
         }
       }
     }
