@@ -256,3 +256,49 @@ def test_errors_are_loud(dev):
     with torch.no_grad():
         m(B.to(dev))
     assert _lib.launch_count() > n0
+
+
+def _bipartite_batch(n_src, n_dst, seed):
+    """One DAG: every one of n_dst sinks has an in-edge from every one of n_src sources (level 0 -> level 1). Forward
+    direction: n_dst nodes with n_src in-edges each; reverse direction: n_src nodes with n_dst in-edges each."""
+    from dagnn_b200 import data as D
+    g = torch.Generator().manual_seed(seed)
+    n = n_src + n_dst
+    src = torch.arange(n_src).repeat_interleave(n_dst)
+    dst = n_src + torch.arange(n_dst).repeat(n_src)
+    ei = torch.stack([src, dst])
+    l0 = torch.cat([torch.zeros(n_src, dtype=torch.long), torch.ones(n_dst, dtype=torch.long)])
+    l1 = 1 - l0
+    ids = torch.arange(n)
+    return D.DagBatch(x=torch.stack([torch.randint(0, 98, (n,), generator=g), torch.randint(0, 10030, (n,), generator=g)], 1),
+                      node_depth=torch.randint(0, 25, (n, 1), generator=g), edge_index=ei,
+                      edge_attr=torch.randint(0, 2, (ei.shape[1], 2), generator=g).float(), batch=torch.zeros(n, dtype=torch.long),
+                      _bi_layer_idx0=l0, _bi_layer_index0=ids.clone(), _bi_layer_idx1=l1, _bi_layer_index1=ids.clone(), num_graphs=1)
+
+
+@pytest.mark.parametrize("n_src,n_dst,hid", [(12, 7300, 32), (40, 300, 64), (3, 70, 520)])
+def test_long_in_edge_lists_and_wide_states(n_src, n_dst, hid, dev):
+    """Gate-phase corner paths: in-edge lists longer than the per-warp limit (whole-CTA aggregation), longer than one
+    32-edge round, more long lists in one CTA than its cooperative queue holds (7300 sinks with 12 in-edges each over 148
+    CTAs: a warp then walks the list alone), lists of thousands of edges (reverse direction), and hidden states wider than
+    one 512-column pass."""
+    from dagnn_b200 import data as D, ogb, runtime as rt
+    from oracle import dagnn_oracle as O
+    B = _bipartite_batch(n_src, n_dst, 5)
+    emb = 24
+    enc = ogb.ASTNodeEncoder(emb, D.CODE2_NUM_NODETYPES, D.CODE2_NUM_NODEATTRS, D.CODE2_MAX_DEPTH)
+    m = ogb.DAGNN(50, 5, emb, hid, None, encoder=enc, num_layers=2, bidirectional=True, out_wx=False, out_pool_all=False)
+    D.deterministic_init_(m, 9)
+    m.eval()
+    with torch.no_grad():
+        _, out_ref, H_ref = O.ogb_forward(state_dict_cpu(m), B, num_layers=2, bidirectional=True, heads=False)
+    m = m.to(dev)
+    with torch.no_grad():
+        X, Hs, sched = m.node_states(B.to(dev))
+        out = m.readout(B.to(dev), X, Hs, sched)
+    st = rt.states_to_node_order(sched, Hs, hid)
+    for d in range(2):
+        for i in range(2):
+            err = (st[d][i].cpu() - H_ref[d][i]).abs().max().item()
+            assert err <= ATOL, "H[%d][%d] max-abs err %g" % (d, i, err)
+    np.testing.assert_allclose(out.cpu().numpy(), out_ref.numpy(), atol=ATOL, rtol=0)
