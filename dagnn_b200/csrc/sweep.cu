@@ -112,14 +112,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of spinning next to the single MMA-issuing thread
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done;
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(a), "r"(parity)
+        : "r"(a), "r"(parity), "r"(0x989680u)
         : "memory");
   } while (!done);
 }
@@ -776,6 +778,9 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   }
   T.p0 = g.pos0 + rt * rows_per;
   T.nrows = min(rows_per, g.n - rt * rows_per);
+  T.nst = (T.nrows + 127) >> 7;
+  T.cb0 = ctile * tb.nbc;
+  T.ncb = min(tb.nbc, nblk - T.cb0);
   if (s >= 0) {
     const int d = it.q / P.layers, i = it.q - d * P.layers;
     T.aimg = P.lay[d][i].aimg + (size_t)((g.pos0 >> 7) + (s - i) + rt * tb.nst) * P.nckh * kAStageBytes;
@@ -785,9 +790,6 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
     const int rp8 = (T.nrows + 7) & ~7;
     if (T.nck * 2 * rp8 * tc::ROW_BYTES <= kNAS * kAStageBytes) T.small = rp8;
   }
-  T.nst = (T.nrows + 127) >> 7;
-  T.cb0 = ctile * tb.nbc;
-  T.ncb = min(tb.nbc, nblk - T.cb0);
   return T;
 }
 // one warp (lanes = segments); the caller publishes the table with a CTA-wide barrier

@@ -1,5 +1,6 @@
+"""Fine-grained stamps of the projection tile of tail steps (needs a -DDAGNN_TRACE_FINE build). GPU box."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from dagnn_b200 import runtime as rt, _lib
@@ -14,9 +15,10 @@ with torch.no_grad():
         Hs, tr = rt.sweep(sched, X, packed, 256, 256, 2, 0, True, trace_steps=steps)
     torch.cuda.synchronize()
 tr = tr.cpu().numpy()[:, :148, :].astype(np.float64) / 1965.0
-for s in (45, 50, 55, 60, 64):
-    t = tr[s]
-    for c in (0, 1, 17, 40):
+for s in (45, 55, 64):
+    t = tr[s + 1]
+    for c in (0, 1, 40, 90):
         if t[c, 6] * 1965 > 0:
-            print("step %d cta %d: rel us: tile-start %.2f | rp-loaded %.2f | scores %.2f | softmax %.2f | pre-done %.2f | b1-loads-issued %.2f | b1-arrived %.2f | build-done %.2f || tr1 %.2f acc %.2f epi-done %.2f all %.2f barrier %.2f" % (
-                s, c, t[c, 8], t[c, 9], t[c, 10], t[c, 11], t[c, 12], t[c, 13], t[c, 14], t[c, 15], t[c,1]-t[c,0], t[c,2]-t[c,0], t[c,3]-t[c,0], t[c,4]-t[c,0], t[c,5]-t[c,0]))
+            print("step %d cta %d (us from phase start): gate-done %.2f | bar1 %.2f || issuer: start %.2f A-issued %.2f B0-landed %.2f A0-landed %.2f all-MMA-issued %.2f || workers: at-epilogue-wait %.2f acc-ready %.2f stored %.2f | bar2 %.2f" % (
+                s, c, t[c, 8] - t[c, 0], t[c, 9] - t[c, 0], t[c, 10], t[c, 11], t[c, 12], t[c, 13], t[c, 14],
+                t[c, 1] - t[c, 0], t[c, 2] - t[c, 0], t[c, 3] - t[c, 0], t[c, 5] - t[c, 0]))
