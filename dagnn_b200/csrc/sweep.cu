@@ -92,6 +92,7 @@ struct SmemTail {
   int ncoop;
   uint64_t a_full[kNAS], a_empty[kNAS], b_full[kNBBar], b_empty[kNBBar], acc_full;
   uint64_t c_full[kMaxChunks];      // small tiles: operand chunk c has landed
+  uint64_t tmem_free;               // the worker warps have drained the accumulators of the previous tile
   uint32_t tmem_slot;
 };
 constexpr size_t kSmemBytes = 1024 + (size_t)kNAS * kAStageBytes + kBRegionBytes + sizeof(SmemTail);
@@ -609,6 +610,8 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
       }
     }
     tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.tmem_free);           // the next tile's MMAs may overwrite the accumulators now
   }
   if (trc) tr[3] = clock64();
 }
@@ -656,7 +659,7 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
 }
 
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
-                                            uint32_t ja, uint32_t cs, RingState& R, const Tile* nextT, int next_nbc) {
+                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc) {
   const int nbs = 8 / nbc;
   const uint32_t idesc = tc::instr_desc_f16(128, 64 * T.ncb);
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
@@ -706,7 +709,8 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
       const uint32_t stage = j % kNAS, use = j / kNAS;
       if (T.small) mbar_wait(&S.c_full[c], cs >> c & 1u);
       else mbar_wait(&S.a_full[stage], use & 1u);
-      tc::fence_after_sync();
+      if (c == 0 && st == 0 && ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);   // operand tiles arrive by bulk copy: nothing
+      tc::fence_after_sync();                                                      // else orders us behind the epilogue
       const uint32_t sa = T.small ? smem_u32(As + (size_t)c * sbytes) : smem_u32(As + (size_t)stage * kAStageBytes);
       const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + (T.small ? sbytes / 2 : 128 * tc::ROW_BYTES));
       const uint32_t tm = tmem + (uint32_t)(st * 64 * nbc);
@@ -846,6 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
     for (int s = 0; s < kNBBar; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
     for (int s = 0; s < kMaxChunks; ++s) mbar_init(&S.c_full[s], 1);
     mbar_init(&S.acc_full, 1);
+    mbar_init(&S.tmem_free, kBuilderWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -945,7 +950,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           hn = tile_advance(tbn, nseg, rank, G, it2);
           if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
         }
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, R, hn ? &N : nullptr, nn);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn);
       }
       __syncwarp();
       if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier
