@@ -19,7 +19,7 @@ HEADERS = ["common.cuh", "tc.cuh"]
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 vp = C.c_void_p
 
@@ -48,7 +48,7 @@ class DagnnSweepArgs(C.Structure):
         ("sched", C.POINTER(DagnnSchedule)),
         ("num_layers", C.c_int32),
         ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32),
-        ("X", vp), ("ldx", C.c_int64),
+        ("X", vp), ("ldx", C.c_int64), ("X_image", vp),
         ("Hs", (vp * MAX_LAYERS) * MAX_DIRS),
         ("ldh", C.c_int64),
         ("packed", (vp * MAX_LAYERS) * MAX_DIRS),
@@ -68,7 +68,8 @@ EXPORTS = {
     "dagnn_abi_version": (C.c_int, []),
     "dagnn_last_error": (C.c_char_p, []),
     "dagnn_launch_count": (C.c_int64, []),
-    "dagnn_embed_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp]),
+    "dagnn_operand_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "dagnn_embed_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
     "dagnn_schedule_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "dagnn_schedule_build": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(DagnnSchedule), vp, C.c_size_t, vp]),
     "dagnn_pack_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DagnnPackLayout)]),

@@ -1,6 +1,7 @@
 // Node encoder (embedding gather-sum) and graph readout (masked segment pool) kernels — both pure HBM/L2
 // streaming work: one coalesced pass, float4 where the layout allows.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace dagnn {
 
@@ -10,7 +11,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) k_embed(const int64_t* __restrict__ x, const int64_t* __restrict__ depth,
                                                const float* __restrict__ T, const float* __restrict__ A,
                                                const float* __restrict__ P, int max_depth, int N, int D,
-                                               float* __restrict__ X, int64_t ldx) {
+                                               float* __restrict__ X, int64_t ldx, unsigned char* __restrict__ ximg) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int v = blockIdx.x * wpb + (threadIdx.x >> 5); v < N; v += gridDim.x * wpb) {
@@ -22,6 +23,16 @@ __global__ void __launch_bounds__(256) k_embed(const int64_t* __restrict__ x, co
     const float* pr = P + (size_t)dp * D;
     float* o = X + (size_t)v * ldx;
     if (VEC4) {
+      // optional second copy of the row: fp16 hi / lo halves in the tcgen05 operand-image layout the sweep's first
+      // projection bulk-copies (128-node tiles x 64-wide k chunks, 32 KB each; k padding zero-filled)
+      const int nck = (D + 63) >> 6;
+      unsigned char* itile = ximg ? ximg + (size_t)(v >> 7) * nck * (2 * 128 * tc::ROW_BYTES) : nullptr;
+      if (itile)
+        for (int c = D + lane * 4; c < nck * 64; c += 128) {
+          unsigned char* ihi = itile + (size_t)(c >> 6) * (2 * 128 * tc::ROW_BYTES) + tc::tile_off(v & 127, (c & 63) >> 3) + (c & 4) * 2;
+          *reinterpret_cast<uint2*>(ihi) = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) = make_uint2(0u, 0u);
+        }
       for (int c = lane * 4; c < D; c += 128) {
         const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + c));
         const float4 av = __ldg(reinterpret_cast<const float4*>(ar + c));
@@ -29,6 +40,15 @@ __global__ void __launch_bounds__(256) k_embed(const int64_t* __restrict__ x, co
         float4 r;
         r.x = tv.x + av.x + pv.x; r.y = tv.y + av.y + pv.y; r.z = tv.z + av.z + pv.z; r.w = tv.w + av.w + pv.w;
         *reinterpret_cast<float4*>(o + c) = r;
+        if (itile) {
+          unsigned char* ihi = itile + (size_t)(c >> 6) * (2 * 128 * tc::ROW_BYTES) + tc::tile_off(v & 127, (c & 63) >> 3) + (c & 4) * 2;
+          const __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(r.x - f0.x, r.y - f0.y), l1 = __floats2half2_rn(r.z - f1.x, r.w - f1.y);
+          *reinterpret_cast<uint2*>(ihi) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
       }
     } else {
       for (int c = lane; c < D; c += 32) o[c] = __ldg(tr + c) + __ldg(ar + c) + __ldg(pr + c);
@@ -109,15 +129,24 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ Readout
 
 using namespace dagnn;
 
+extern "C" size_t dagnn_operand_image_bytes(int64_t N, int32_t D) {
+  if (N < 0 || D < 1) return 0;
+  return (size_t)((N + 127) >> 7) * (size_t)((D + 63) >> 6) * (2 * 128 * tc::ROW_BYTES);
+}
+
 extern "C" int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
-                               const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* stream_) {
+                               const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* x_image,
+                               void* stream_) {
   DAGNN_REQUIRE(x && depth && type_tab && attr_tab && depth_tab && X, "embed: null pointer");
   DAGNN_REQUIRE(N > 0 && N < (1ll << 31) && D > 0 && ldx >= D && max_depth >= 0, "embed: sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && ((((uintptr_t)type_tab | (uintptr_t)attr_tab | (uintptr_t)depth_tab | (uintptr_t)X) & 15) == 0);
+  if (x_image && (!vec || ((uintptr_t)x_image & 1023) != 0))
+    return set_err(DAGNN_E_INVALID, "embed: the operand image needs D %% 4 == 0, 16-byte aligned tables / X and a 1024-byte aligned image");
   const int blocks = (int)((N + 7) / 8 < 148 * 16 ? (N + 7) / 8 : 148 * 16);
-  if (vec) k_embed<true><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx);
-  else k_embed<false><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx);
+  if (vec) k_embed<true><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx,
+                                                  static_cast<unsigned char*>(x_image));
+  else k_embed<false><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx, nullptr);
   return check_launch("k_embed");
 }
 

@@ -55,6 +55,7 @@ struct LayP {
   float* sk;            // [N] key score wk . h of every node
   float* Pm;            // [N, Mc] W_hh^i h^i_j  (columns gate * Hq + unit)
   float* Gi;            // [N, Mc] W_ih^i inp_v
+  const int* gi_perm;   // non-null: Gi is in NODE order (layer 0 projected from the X image): row of position p = gi_perm[p]
   const float* bias;    // [4][HP]
   const float* wk;      // [HP]
   const float* attnc;   // [4]
@@ -69,6 +70,7 @@ struct SweepP {
   int vec_x, N, Kh64;
   long long ldh, ldx;
   const float* X;             // [N, ldx] node order (rows through perm)
+  const unsigned char* ximg;  // optional operand image of X in node order: the first projection then runs in node order
   const int* summary;         // [0] number of levels of direction 0, [2] schedule status
   unsigned int* bar;          // grid barrier counter (zeroed by the launcher)
   long long* trace;           // optional [steps + 1][256][16] clock64 stamps, nullptr = off
@@ -218,7 +220,7 @@ struct GiRow {                     // the node's own input projection, lane's un
 };
 template <int J>
 __device__ __forceinline__ void load_gi(GiRow<J>& Gr, const SweepP& P, const LayP& Lp, int p, int ub, int lane) {
-  const float* __restrict__ gi = Lp.Gi + (size_t)p * P.Mc;
+  const float* __restrict__ gi = Lp.Gi + (size_t)(Lp.gi_perm ? Lp.gi_perm[p] : p) * P.Mc;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < J; ++j) {
@@ -770,7 +772,7 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   Tile T;
   if (s < 0) {
     const int d = it.q;
-    T.A = P.X; T.lda = P.ldx; T.perm = P.dir[d].perm; T.img = P.lay[d][0].imgx; T.aimg = nullptr;
+    T.A = P.X; T.lda = P.ldx; T.perm = P.ximg ? nullptr : P.dir[d].perm; T.img = P.lay[d][0].imgx; T.aimg = nullptr;
     T.out0 = P.lay[d][0].Gi; T.out1 = nullptr;
     T.K = P.Din0; T.nck = P.nckx; T.vec = P.vec_x;
   } else {
@@ -788,6 +790,8 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   if (s >= 0) {
     const int d = it.q / P.layers, i = it.q - d * P.layers;
     T.aimg = P.lay[d][i].aimg + (size_t)((g.pos0 >> 7) + (s - i) + rt * tb.nst) * P.nckh * kAStageBytes;
+  } else if (P.ximg) {
+    T.aimg = P.ximg + (size_t)(rt * tb.nst) * P.nckx * kAStageBytes;       // rows = nodes, tiles of 128 nodes
   }
   T.small = 0;
   if (T.aimg && T.nst == 1 && T.nck <= kMaxChunks) {
@@ -1015,6 +1019,8 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   P.N = (int)S->N; P.Kh64 = lay[0].Kh64;
   P.ldh = A->ldh; P.ldx = A->ldx; P.X = A->X; P.summary = S->summary; P.bar = static_cast<unsigned int*>(A->workspace);
   P.trace = static_cast<long long*>(A->trace);
+  P.ximg = static_cast<const unsigned char*>(A->X_image);
+  DAGNN_REQUIRE(!P.ximg || ((uintptr_t)P.ximg & 1023) == 0, "sweep: X_image must be 1024-byte aligned");
   char* ws = static_cast<char*>(A->workspace) + 256;
   const size_t sk_bytes = align256((size_t)S->N * sizeof(float)), pm_bytes = align256((size_t)S->N * P.Mc * sizeof(float));
   for (int d = 0; d < dirs; ++d) {
@@ -1031,6 +1037,7 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
       q.Hs = A->Hs[d][i]; q.bias = pk + L.bias_off; q.wk = pk + L.wk_off; q.attnc = pk + L.attnc_off; q.vidk = pk + L.vidk_off;
       q.imgh = reinterpret_cast<const __half*>(pk + L.imgh_off);
       q.imgx = i == 0 ? reinterpret_cast<const __half*>(pk + L.imgx_off) : nullptr;
+      q.gi_perm = (i == 0 && P.ximg) ? S->perm[d] : nullptr;
       q.sk = reinterpret_cast<float*>(ws); ws += sk_bytes;
       q.Pm = reinterpret_cast<float*>(ws); ws += pm_bytes;
       q.Gi = reinterpret_cast<float*>(ws); ws += pm_bytes;

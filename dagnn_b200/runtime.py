@@ -39,14 +39,21 @@ def _align(n: int, a: int = 64) -> int:
 
 
 def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, max_depth: int) -> torch.Tensor:
-    """ASTNodeEncoder.forward (ogbg-code/utils.py:26-28) -> fp32 [N, D]."""
+    """ASTNodeEncoder.forward (ogbg-code/utils.py:26-28) -> fp32 [N, D]. When D % 4 == 0 the kernel also writes the
+    operand image of X for the sweep's first projection; it rides on the returned tensor as `._dagnn_image`."""
     x = _req_cuda(x, "x", torch.int64)
     depth = _req_cuda(depth.view(-1), "node_depth", torch.int64)
     T, A, P = (_req_cuda(t.detach(), "embedding table", torch.float32) for t in (type_tab, attr_tab, depth_tab))
     N, D = x.shape[0], T.shape[1]
     X = torch.empty(N, D, device=x.device, dtype=torch.float32)
+    img = None
+    if D % 4 == 0:
+        img = torch.empty(int(lib().dagnn_operand_image_bytes(N, D)) + 1024, device=x.device, dtype=torch.uint8)
+        off = (-img.data_ptr()) % 1024
+        img = img[off: off + int(lib().dagnn_operand_image_bytes(N, D))]
     check(lib().dagnn_embed_f32(_ptr(x), _ptr(depth), _ptr(T), _ptr(A), _ptr(P), int(max_depth), N, D, _ptr(X), D,
-                                _stream()), "dagnn_embed_f32")
+                                _ptr(img), _stream()), "dagnn_embed_f32")
+    X._dagnn_image = img
     return X
 
 
@@ -278,6 +285,8 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
     a.num_layers = num_layers
     a.Din, a.H, a.nvid = Din, H, nvid
     a.X, a.ldx, a.ldh = X.data_ptr(), X.stride(0), ldh
+    ximg = getattr(X, "_dagnn_image", None)
+    a.X_image = ximg.data_ptr() if ximg is not None else None
     a.use_edge_attr = 1 if use_edge_attr else 0
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     trace = None

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 4
+#define DAGNN_ABI_VERSION 5
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -51,9 +51,14 @@ int64_t dagnn_launch_count(void);
  * replaces ASTNodeEncoder.forward, ogbg-code/utils.py:26-28 (called at ogbg-code/model/dagnn.py:139).
  * x int64 [N,2] row-major, depth int64 [N]; tables fp32 row-major with leading dimension D; X fp32 [N, ldx].
  * Unlike the reference it does not clamp `depth` in place.
+ * x_image (optional, NULL = off): a second copy of X as fp16 hi / lo halves in the tcgen05 operand-image layout
+ * (128-node tiles x 64-wide k chunks, dagnn_operand_image_bytes(N, D) bytes, 1024-byte aligned; needs D % 4 == 0) that
+ * dagnn_sweep_forward_f32 can bulk-copy for its first projection (DagnnSweepArgs.X_image).
  * --------------------------------------------------------------------------------------------------------- */
+size_t dagnn_operand_image_bytes(int64_t N, int32_t D);
 int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
-                    const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* stream);
+                    const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* x_image,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Integer pre-pass (bit-exact): level-sorted node order + in-edge CSR per direction.
@@ -149,6 +154,7 @@ typedef struct DagnnSweepArgs {
   int32_t Din, H, nvid;                /* input width, hidden width, #vertex-id columns (0 = none) */
   const float* X;                      /* [N, ldx] node features in NODE order                      */
   int64_t ldx;
+  const void* X_image;                 /* optional operand image of X (dagnn_embed_f32), NULL = X rows are gathered */
   float* Hs[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];               /* [N, ldh] each, position order      */
   int64_t ldh;                         /* >= roundup(H,4), multiple of 4                            */
   const float* packed[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];     /* dagnn_pack_params_f32 outputs       */
