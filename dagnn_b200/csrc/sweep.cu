@@ -137,6 +137,8 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // Only the builder warps write global memory, so they alone gate the arrival (named barrier 1); the issuer warp, which may
 // still be queueing weight prefetches, joins at the closing CTA-wide barrier.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  // state rows written with ordinary stores are read after the barrier by other CTAs' bulk copies (async proxy)
+  asm volatile("fence.proxy.async;" ::: "memory");
   if (threadIdx.x < kBuilders) asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   if (threadIdx.x == 0) {
     __threadfence();
