@@ -41,6 +41,8 @@ constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 co
 constexpr int kMaxChunks = 16;                           // k chunks of a tile that may use compact operand stages
 constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (8 warps split the edge list)
 constexpr int kMaxCoop = 48;       // ... per CTA and gate phase; beyond that a warp does the node alone
+constexpr int kScanRows = 2048;    // steps with at most this many rows are latency-bound: their long in-edge lists are found a
+constexpr int kMaxHeavy = 128;     // phase ahead (at most this many) and get a CTA of their own, from the start of the phase
 constexpr int kMaxSmem = 232448;                         // 227 KB opt-in limit per CTA on sm_100
 
 struct DirP {
@@ -80,11 +82,25 @@ struct SweepP {
 
 struct Seg {
   int pos0, n, ntile, base;
+  int bmod;                   // base % grid size: the tile loop of a CTA starts without a division
+  int ncbt;                   // column tiles per row tile
+  uint32_t rcbt;              // ceil(2^32 / ncbt), ncbt > 1: t / ncbt == __umulhi(t, rcbt) for t * ncbt < 2^32
 };
+// no runtime integer division in the per-step paths: every thread runs them, ~130 times per forward, and a division is
+// ~50 instructions of dependent latency and of instruction-cache footprint
+__device__ __forceinline__ void seg_di(const SweepP& P, int q, int& d, int& i) {     // q = d * layers + i, d < 2
+  d = (q >= P.layers) ? 1 : 0;
+  i = d ? q - P.layers : q;
+}
+__device__ __forceinline__ int blk_shift(int nbc) { return nbc >> 1; }               // log2 of 1, 2, 4
 struct StepTab {
   Seg seg[kMaxSeg];           // projection of step s: rows to project (empty when nothing downstream needs them)
   int gpos0[kMaxSeg], gn[kMaxSeg];   // gate phase of step s: first position and rows of every segment's level
   int nbc, nst;               // 64-column blocks per tile (1, 2, 4), 128-row sub-tiles per tile
+};
+struct HeavyTab {
+  int n;                      // gate phase of step s: nodes with more than kCoopEdges in-edges, -1 = not scanned
+  int node[kMaxHeavy][2];     // ... their (segment, position), segment-major, positions ascending
 };
 constexpr int kEpiLd = 20;    // floats per scratch row: 16 columns + pad (16-byte aligned rows)
 struct SmemTail {
@@ -96,6 +112,7 @@ struct SmemTail {
   uint64_t c_full[kMaxChunks];      // small tiles: operand chunk c has landed
   uint64_t tmem_free;               // the worker warps have drained the accumulators of the previous tile
   uint32_t tmem_slot;
+  HeavyTab heavy[2];                // long in-edge lists of this gate phase and the next one
 };
 constexpr size_t kSmemBytes = 1024 + (size_t)kNAS * kAStageBytes + kBRegionBytes + sizeof(SmemTail);
 static_assert(kSmemBytes <= (size_t)kMaxSmem, "shared memory plan exceeds the 227 KB opt-in limit");
@@ -177,21 +194,45 @@ struct GateRows {                  // projected + state rows of one in-edge, lan
 template <int J>
 __device__ __forceinline__ void load_rows(GateRows<J>& R, const float* __restrict__ Pm, const float* __restrict__ Hs, int sp, bool on,
                                           int Mc, long long ldh, int Hq, int ub, int lane) {
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // one warp-uniform branch per in-edge (an in-edge that adds nothing is not read: its row may not have been written
+  // yet), nothing predicated inside: 4 J independent 16-byte loads per lane that go out back to back. The units past Hq
+  // of the last column pass re-read the first ones (gate_finish ignores them).
   const float* pr = Pm + (size_t)sp * Mc;
   const float* hr = Hs + (size_t)sp * ldh;
+  if (on) {
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int u = ub + 4 * lane + 128 * j;
-    R.r[j] = z4; R.z[j] = z4; R.n[j] = z4; R.h[j] = z4;
-    if (on && u < Hq) {
+    for (int j = 0; j < J; ++j) {
+      int u = ub + 4 * lane + 128 * j;
+      u = (u < Hq) ? u : 4 * lane;
       R.r[j] = ldcg4(pr + u);
       R.z[j] = ldcg4(pr + Hq + u);
       R.n[j] = ldcg4(pr + 2 * Hq + u);
       R.h[j] = ldcg4(hr + u);
     }
+  } else {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < J; ++j) { R.r[j] = z4; R.z[j] = z4; R.n[j] = z4; R.h[j] = z4; }
   }
 }
+
+// Scheduling fence. ptxas sinks the loads of a row next to the FMAs that consume it to save registers; with in-order
+// issue the warp then stalls on the first FMA before the next loads have gone out — three or four dependent L2 round
+// trips per in-edge pair instead of one. rows_zero() is 0 computed from one word of every 16-byte load (x * 0, not
+// foldable: x could be a NaN); adding it to the softmax weights makes every FMA wait for every load, so nothing is gained
+// by delaying a load and they issue back to back. (A non-finite state poisons the sums either way.)
+template <int J>
+__device__ __forceinline__ float rows_zero(const GateRows<J>& R, float t) {
+#ifdef DAGNN_NO_FENCE
+  return t;
+#endif
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    t = fmaf(R.r[j].x, 0.f, t); t = fmaf(R.z[j].x, 0.f, t); t = fmaf(R.n[j].x, 0.f, t); t = fmaf(R.h[j].x, 0.f, t);
+  }
+  return t;
+}
+
 template <int J>
 __device__ __forceinline__ void add_rows(GateAcc (&A)[J], float a, const GateRows<J>& R) {
 #pragma unroll
@@ -279,9 +320,20 @@ __device__ __forceinline__ float gate_finish(const SweepP& P, const LayP& Lp, in
   return skacc;
 }
 
+// -DDAGNN_GATE_TRACE (profiling builds only): lane 0 of warp 0 stamps the stages of the first node it handles in a step
+// into trace slots 10..15; the stamp is ordered behind the value named as its dependency
+#ifdef DAGNN_GATE_TRACE
+#define DAGNN_GT(slot, dep)                                                                         \
+  if (gt) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(dep) : "memory"); gt[slot] = t_; }
+#define DAGNN_GT_ARG , long long* gt
+#else
+#define DAGNN_GT(slot, dep)
+#define DAGNN_GT_ARG
+#endif
+
 // one warp, one node
 template <int J>
-__device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, int lane) {
+__device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, int lane DAGNN_GT_ARG) {
   const bool level0 = lvl == 0;
   const int Hq = P.Hq, Mc = P.Mc;
   const long long ldh = P.ldh;
@@ -293,6 +345,7 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
   int e0 = 0, e1 = 0;
   if (!level0) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
   const int ne = e1 - e0;
+  DAGNN_GT(11, ne)
   float skacc = 0.f;
   if (ne <= 32) {
     // ---- the common case: all in-edges in one round, one lane per edge
@@ -300,6 +353,7 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
     float my_sc = -INFINITY;
     if (lane < ne) my_sc = edge_score(P, D, Lp, e0 + lane, pos0, ca0, ca1, use_ea, my_sp);
     const bool my_valid = lane < ne && my_sp < pos0;
+    DAGNN_GT(12, __float_as_int(my_sc))
 #pragma unroll 1
     for (int ub = 0; ub < Hq; ub += 128 * J) {
       GateAcc A[J];
@@ -320,6 +374,7 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
         const float ex = (lane < ne) ? expf(my_sc - mx) : 0.f;
         const float inv = 1.f / (warp_sum(ex) + 1e-16f);
         const float my_a = my_valid ? ex * inv : 0.f;
+        DAGNN_GT(13, __float_as_int(R0.r[0].x))
         add_rows<J>(A, __shfl_sync(0xffffffffu, my_a, 0), R0);
         if constexpr (kTwo) {
           add_rows<J>(A, __shfl_sync(0xffffffffu, my_a, 1), R1);
@@ -328,8 +383,9 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
             const int s0 = __shfl_sync(0xffffffffu, my_sp, q), s1 = __shfl_sync(0xffffffffu, my_sp, (q + 1) & 31);
             load_rows<J>(R0, Pm, Hs, s0, a0 != 0.f, Mc, ldh, Hq, ub, lane);
             load_rows<J>(R1, Pm, Hs, s1, a1 != 0.f && q + 1 < ne, Mc, ldh, Hq, ub, lane);
-            add_rows<J>(A, a0, R0);
-            add_rows<J>(A, (q + 1 < ne) ? a1 : 0.f, R1);
+            const float t0 = rows_zero<J>(R1, rows_zero<J>(R0, 0.f));
+            add_rows<J>(A, a0 + t0, R0);
+            add_rows<J>(A, ((q + 1 < ne) ? a1 : 0.f) + t0, R1);
           }
         } else {
           (void)sp1; (void)v1;
@@ -338,11 +394,12 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
             const int s0 = __shfl_sync(0xffffffffu, my_sp, q);
             if (a0 == 0.f) continue;
             load_rows<J>(R0, Pm, Hs, s0, true, Mc, ldh, Hq, ub, lane);
-            add_rows<J>(A, a0, R0);
+            add_rows<J>(A, a0 + rows_zero<J>(R0, 0.f), R0);
           }
         }
       }
       if constexpr (J > 2) load_gi<J>(Gr, P, Lp, p, ub, lane);
+      DAGNN_GT(14, __float_as_int(Gr.r[0].x + A[0].r.x))
       skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A, Gr);
     }
   } else {
@@ -377,7 +434,7 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
           if (a == 0.f) continue;                            // warp-uniform
           GateRows<J> R0;
           load_rows<J>(R0, Pm, Hs, sp, true, Mc, ldh, Hq, ub, lane);
-          add_rows<J>(A, a, R0);
+          add_rows<J>(A, a + rows_zero<J>(R0, 0.f), R0);
         }
       }
       GiRow<J> Gr;
@@ -387,97 +444,108 @@ __device__ __forceinline__ void gate_row(const SweepP& P, const DirP& D, const L
   }
   skacc = warp_sum(skacc);
   if (lane == 0) Lp.sk[p] = skacc;
+  DAGNN_GT(15, __float_as_int(skacc))
 }
 
-// the whole CTA (kBuilderWarps warps), one node with a long in-edge list: every warp derives the softmax statistics
-// (redundantly, in parallel), aggregates every kBuilderWarps-th in-edge, the partial sums meet in shared memory and
-// warp 0 finishes the node. `part` = [kBuilderWarps][4][128 J] floats of shared memory.
-template <int J>
-__device__ __noinline__ void gate_row_coop(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, float* part,
-                                              int warp, int lane) {
-  const int Hq = P.Hq, Mc = P.Mc;
+// the whole CTA (kBuilderWarps warps), one node with a long in-edge list, split by COLUMNS: thread t owns the units
+// t + 256 k, so a predecessor costs a lane four 4-byte loads (P_r, P_z, P_n, h of its unit; 128 contiguous bytes per warp),
+// eight predecessors are in flight per lane, nothing is reduced across warps and the GRU pointwise work is one unit per
+// thread. Every warp derives the softmax weights itself (one lane per in-edge, 32 consecutive in-edges per round; the
+// scores of the only round stay in registers). `part` = kBuilderWarps floats of shared memory for the key score.
+__device__ __noinline__ void gate_node_cta(const SweepP& P, const DirP& D, const LayP& Lp, int p, int pos0, int lvl, float* part,
+                                           int warp, int lane DAGNN_GT_ARG) {
+  DAGNN_GT(10, lane)
+  const int Hq = P.Hq, HP = P.HP, Mc = P.Mc;
   const long long ldh = P.ldh;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool use_ea = P.use_ea && D.eattr != nullptr;
   const float ca0 = use_ea ? __ldg(Lp.attnc) : 0.f, ca1 = use_ea ? __ldg(Lp.attnc + 1) : 0.f;
   const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
-  float sum = 0.f, mx = -INFINITY;
+  const bool one_round = e1 - e0 <= 32;
+  float sum = 0.f, mx = -INFINITY, sc0 = -INFINITY;
+  int sp0 = 0;
   for (int eb = e0; eb < e1; eb += 32) {
     const int e = eb + lane;
-    int sp;
-    const float sc = (e < e1) ? edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, sp) : -INFINITY;
-    const float mnew = fmaxf(mx, warp_max(sc));
-    sum = sum * expf(mx - mnew) + warp_sum((e < e1) ? expf(sc - mnew) : 0.f);
+    sc0 = (e < e1) ? edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, sp0) : -INFINITY;
+    const float mnew = fmaxf(mx, warp_max(sc0));
+    sum = sum * expf(mx - mnew) + warp_sum((e < e1) ? expf(sc0 - mnew) : 0.f);
     mx = mnew;
   }
   const float inv = 1.f / (sum + 1e-16f);
+  DAGNN_GT(11, __float_as_int(inv))
+  const int rel = p - pos0, rin = rel & 127;
+  unsigned char* itile = Lp.aimg + (size_t)((pos0 >> 7) + lvl + (rel >> 7)) * P.nckh * kAStageBytes;
+  const float* __restrict__ gi = Lp.Gi + (size_t)(Lp.gi_perm ? Lp.gi_perm[p] : p) * Mc;
   float skacc = 0.f;
 #pragma unroll 1
-  for (int ub = 0; ub < Hq; ub += 128 * J) {
-    GateAcc A[J];
+  for (int ub = 0; ub < P.Kh64; ub += kBuilders) {
+    const int u = ub + 32 * warp + lane;
+    const bool live = u < Hq;
+    const int uc = live ? u : 0;                        // idle threads of the last pass read unit 0 and drop it
+    const float gr = __ldcg(gi + uc), gz = __ldcg(gi + Hq + uc), gn = __ldcg(gi + 2 * Hq + uc);   // in flight from the start
+    float ar = 0.f, az = 0.f, an = 0.f, am = 0.f;
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int e = eb + lane;
+      int my_sp = sp0;
+      float sc = sc0;
+      if (!one_round) sc = (e < e1) ? edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, my_sp) : -INFINITY;
+      const float my_a = (e < e1 && my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
+      if (my_a == 0.f) my_sp = 0;                       // adds nothing: row 0 (written, finite) stands in, its own may not be
+      const int nq = min(32, e1 - eb);
+      for (int q = 0; q < nq; q += 8) {
+        float a[8], vr[8], vz[8], vn[8], vh[8];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { A[j].r = z4; A[j].z = z4; A[j].n = z4; A[j].m = z4; }
-    // this warp's in-edges: e0 + warp + kBuilderWarps * t, one lane per t
-    for (int eb = e0 + warp; eb < e1; eb += 32 * kBuilderWarps) {
-      const int e = eb + kBuilderWarps * lane;
-      int my_sp = 0;
-      float my_a = 0.f;
-      if (e < e1) {
-        const float sc = edge_score(P, D, Lp, e, pos0, ca0, ca1, use_ea, my_sp);
-        my_a = (my_sp < pos0) ? expf(sc - mx) * inv : 0.f;
-      }
-      const int nq = min(32, (e1 - eb + kBuilderWarps - 1) / kBuilderWarps);
-      if constexpr (J <= 2) {
-        for (int q = 0; q < nq; q += 2) {
-          const float a0 = __shfl_sync(0xffffffffu, my_a, q), a1 = __shfl_sync(0xffffffffu, my_a, (q + 1) & 31);
-          const int s0 = __shfl_sync(0xffffffffu, my_sp, q), s1 = __shfl_sync(0xffffffffu, my_sp, (q + 1) & 31);
-          GateRows<J> R0, R1;
-          load_rows<J>(R0, Lp.Pm, Lp.Hs, s0, a0 != 0.f, Mc, ldh, Hq, ub, lane);
-          load_rows<J>(R1, Lp.Pm, Lp.Hs, s1, a1 != 0.f && q + 1 < nq, Mc, ldh, Hq, ub, lane);
-          add_rows<J>(A, a0, R0);
-          add_rows<J>(A, (q + 1 < nq) ? a1 : 0.f, R1);
+        for (int k = 0; k < 8; ++k) {
+          a[k] = __shfl_sync(0xffffffffu, my_a, (q + k) & 31);
+          const int sp = __shfl_sync(0xffffffffu, my_sp, (q + k) & 31);
+          const float* pr = Lp.Pm + (size_t)sp * Mc + uc;
+          vr[k] = __ldcg(pr); vz[k] = __ldcg(pr + Hq); vn[k] = __ldcg(pr + 2 * Hq);
+          vh[k] = __ldcg(Lp.Hs + (size_t)sp * ldh + uc);
         }
-      } else {
-        for (int q = 0; q < nq; ++q) {
-          const float a0 = __shfl_sync(0xffffffffu, my_a, q);
-          const int s0 = __shfl_sync(0xffffffffu, my_sp, q);
-          if (a0 == 0.f) continue;
-          GateRows<J> R0;
-          load_rows<J>(R0, Lp.Pm, Lp.Hs, s0, true, Mc, ldh, Hq, ub, lane);
-          add_rows<J>(A, a0, R0);
+        float t0 = 0.f;                                 // scheduling fence, see rows_zero()
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          t0 = fmaf(vr[k], 0.f, t0); t0 = fmaf(vz[k], 0.f, t0); t0 = fmaf(vn[k], 0.f, t0); t0 = fmaf(vh[k], 0.f, t0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float w = a[k] + t0;
+          ar = fmaf(w, vr[k], ar); az = fmaf(w, vz[k], az); an = fmaf(w, vn[k], an); am = fmaf(w, vh[k], am);
         }
       }
     }
-    float4* mine = reinterpret_cast<float4*>(part) + (size_t)warp * 4 * 32 * J;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      mine[(0 * J + j) * 32 + lane] = A[j].r; mine[(1 * J + j) * 32 + lane] = A[j].z;
-      mine[(2 * J + j) * 32 + lane] = A[j].n; mine[(3 * J + j) * 32 + lane] = A[j].m;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
-    if (warp == 0) {
-      for (int w = 1; w < kBuilderWarps; ++w) {
-        const float4* o = reinterpret_cast<const float4*>(part) + (size_t)w * 4 * 32 * J;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const float4 r = o[(0 * J + j) * 32 + lane], z = o[(1 * J + j) * 32 + lane], n = o[(2 * J + j) * 32 + lane],
-                       m = o[(3 * J + j) * 32 + lane];
-          A[j].r.x += r.x; A[j].r.y += r.y; A[j].r.z += r.z; A[j].r.w += r.w;
-          A[j].z.x += z.x; A[j].z.y += z.y; A[j].z.z += z.z; A[j].z.w += z.w;
-          A[j].n.x += n.x; A[j].n.y += n.y; A[j].n.z += n.z; A[j].n.w += n.w;
-          A[j].m.x += m.x; A[j].m.y += m.y; A[j].m.z += m.z; A[j].m.w += m.w;
-        }
+    DAGNN_GT(12, __float_as_int(ar))
+    if (u < P.Kh64) {
+      unsigned char* ihi = itile + (size_t)(u >> 6) * kAStageBytes + tc::tile_off(rin, (u & 63) >> 3) + (u & 7) * 2;
+      __half hh = __float2half_rn(0.f), hl = hh;        // k padding of the last chunk: zeros
+      if (live) {
+        const float br = __ldg(Lp.bias + u), bz = __ldg(Lp.bias + HP + u), bi = __ldg(Lp.bias + 2 * HP + u),
+                    bh = __ldg(Lp.bias + 3 * HP + u);
+        const float rg = fast_sigmoid(gr + ar + br);
+        const float zg = fast_sigmoid(gz + az + bz);
+        const float ng = fast_tanh(gn + bi + rg * (an + bh));
+        const float o = ng + zg * (am - ng);
+        Lp.Hs[(size_t)p * ldh + u] = o;
+        hh = __float2half_rn(o);
+        hl = __float2half_rn(o - __half2float(hh));
+        skacc += o * __ldg(Lp.wk + u);
       }
-      GiRow<J> Gr;
-      load_gi<J>(Gr, P, Lp, p, ub, lane);
-      skacc += gate_finish<J>(P, Lp, p, pos0, lvl, ub, lane, A, Gr);
+      *reinterpret_cast<__half*>(ihi) = hh;
+      *reinterpret_cast<__half*>(ihi + 128 * tc::ROW_BYTES) = hl;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   }
-  if (warp == 0) {
-    skacc = warp_sum(skacc);
-    if (lane == 0) Lp.sk[p] = skacc;
+  DAGNN_GT(13, __float_as_int(skacc))
+  skacc = warp_sum(skacc);
+  if (lane == 0) part[warp] = skacc;
+  asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+  DAGNN_GT(14, lane)
+  if (warp == 0 && lane == 0) {
+    float sk = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBuilderWarps; ++w) sk += part[w];
+    Lp.sk[p] = sk;
   }
+  asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+  DAGNN_GT(15, lane)
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -519,7 +587,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
   auto groups_of = [&](int st) { return min(kNR, (min(128, T.nrows - st * 128) + kRStride - 1) / kRStride); };
   auto prefetch = [&](int it, Pre& R) {
     if (it >= nitems) return;
-    const int c = it / T.nst, st = it - c * T.nst;
+    const int c = it >> (T.nst - 1), st = it & (T.nst - 1);
     const int nx = groups_of(st);
     const int k0 = c * tc::KC16 + 8 * c8;
 #pragma unroll
@@ -547,7 +615,7 @@ __device__ __forceinline__ void builder_tile(const SweepP& P, const Tile& T, uns
   if (!T.aimg) prefetch(0, R);
 #pragma unroll 1
   for (int it = 0; it < (T.aimg ? 0 : nitems); ++it) {
-    const int st = it % T.nst;
+    const int st = it & (T.nst - 1);
     const uint32_t j = ja + (uint32_t)it;
     const uint32_t stage = j % kNAS, use = j / kNAS;
     unsigned char* A_hi = As + (size_t)stage * kAStageBytes;
@@ -644,7 +712,7 @@ __device__ __forceinline__ void ring_set_geometry(int nbc, SmemTail& S, RingStat
 }
 // weight chunk c of a tile -> next ring stage: hi tiles of the tile's blocks, then their lo tiles
 __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigned char* Bs, SmemTail& S, RingState& R) {
-  const uint32_t nbs = 8u / (uint32_t)nbc;
+  const uint32_t nbs = 8u >> blk_shift(nbc);
   const uint32_t s = R.next;
   R.next = (s + 1 == nbs) ? 0u : s + 1;
   if (R.pending >> s & 1u) {                         // MMAs that read this stage must be done
@@ -664,7 +732,7 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
 
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
                                             uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc) {
-  const int nbs = 8 / nbc;
+  const int nbs = 8 >> blk_shift(nbc);
   const uint32_t idesc = tc::instr_desc_f16(128, 64 * T.ncb);
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
   // was still computing, or before a grid barrier)
@@ -677,7 +745,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   // (hi, lo) of the rows the sub-tile really has, rounded up to the 8-row swizzle group
   const int nitems = T.nck * T.nst;
   auto load_A = [&](int it) {
-    const int c = it / T.nst, st = it - c * T.nst;
+    const int c = it >> (T.nst - 1), st = it & (T.nst - 1);
     const uint32_t j = ja + (uint32_t)it;
     const uint32_t stage = j % kNAS, use = j / kNAS;
     if (use >= 1) mbar_wait(&S.a_empty[stage], (use - 1) & 1u);        // MMAs that read this stage are done
@@ -702,7 +770,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   }
 #pragma unroll 1
   for (int c = 0; c < T.nck; ++c) {
-    const uint32_t s = (first + (uint32_t)c) % (uint32_t)nbs;
+    const uint32_t s = (first + (uint32_t)c) & (uint32_t)(nbs - 1);
     mbar_wait(&S.b_full[s], R.full_par >> s & 1u);
     R.full_par ^= 1u << s;
     const uint32_t sb = smem_u32(Bs + (size_t)s * nbc * kBlkBytes);
@@ -736,7 +804,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   if (nextT) {
     ring_set_geometry(next_nbc, S, R);
     R.pre_first = R.next;
-    const int n2 = min(8 / next_nbc, nextT->nck);
+    const int n2 = min(8 >> blk_shift(next_nbc), nextT->nck);
     for (int c = 0; c < n2; ++c) ring_load(*nextT, next_nbc, c, Bs, S, R);
     R.pre = (uint32_t)n2;
   }
@@ -749,16 +817,17 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
 struct TileIt { int q, t; };
 
 __device__ __forceinline__ int seg_blocks(const SweepP& P, int s, int q) {      // 64-column blocks of segment q's projection
-  const int mb = P.Mc / 64;
+  const int mb = P.Mc >> 6;
   if (s < 0) return mb;                                 // X -> Gi^0
-  const int i = q % P.layers;
+  int d, i;
+  seg_di(P, q, d, i);
   return (i + 1 < P.layers) ? 2 * mb : mb;              // H^i -> P^i [, Gi^{i+1}]
 }
 __device__ __forceinline__ bool tile_advance(const StepTab& tb, int nseg, int rank, int G, TileIt& it) {
   if (it.t >= 0) it.t += G;
   while (it.q < nseg) {
     const Seg g = tb.seg[it.q];
-    if (it.t < 0) it.t = ((rank - g.base) % G + G) % G;     // my tiles of a segment: global ids base + t with (base + t) % G == rank
+    if (it.t < 0) it.t = (rank >= g.bmod) ? rank - g.bmod : rank - g.bmod + G;     // my tiles of a segment: (base + t) % G == rank
     if (it.t < g.ntile) return true;
     ++it.q;
     it.t = -1;
@@ -768,9 +837,9 @@ __device__ __forceinline__ bool tile_advance(const StepTab& tb, int nseg, int ra
 __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, int s, const TileIt& it) {
   const Seg g = tb.seg[it.q];
   const int nblk = seg_blocks(P, s, it.q);
-  const int ncbt = ceil_div(nblk, tb.nbc);              // column tiles per row tile
+  const int ncbt = g.ncbt;                              // column tiles per row tile
   const int rows_per = 128 * tb.nst;
-  const int rt = it.t / ncbt, ctile = it.t - rt * ncbt;
+  const int rt = (ncbt == 1) ? it.t : (int)__umulhi((uint32_t)it.t, g.rcbt), ctile = it.t - rt * ncbt;
   Tile T;
   if (s < 0) {
     const int d = it.q;
@@ -778,7 +847,8 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
     T.out0 = P.lay[d][0].Gi; T.out1 = nullptr;
     T.K = P.Din0; T.nck = P.nckx; T.vec = P.vec_x;
   } else {
-    const int d = it.q / P.layers, i = it.q - d * P.layers;
+    int d, i;
+    seg_di(P, it.q, d, i);
     const LayP& Lp = P.lay[d][i];
     T.A = Lp.Hs; T.lda = P.ldh; T.perm = nullptr; T.img = Lp.imgh;
     T.out0 = Lp.Pm; T.out1 = (i + 1 < P.layers) ? P.lay[d][i + 1].Gi : nullptr;
@@ -790,7 +860,8 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   T.cb0 = ctile * tb.nbc;
   T.ncb = min(tb.nbc, nblk - T.cb0);
   if (s >= 0) {
-    const int d = it.q / P.layers, i = it.q - d * P.layers;
+    int d, i;
+    seg_di(P, it.q, d, i);
     T.aimg = P.lay[d][i].aimg + (size_t)((g.pos0 >> 7) + (s - i) + rt * tb.nst) * P.nckh * kAStageBytes;
   } else if (P.ximg) {
     T.aimg = P.ximg + (size_t)(rt * tb.nst) * P.nckx * kAStageBytes;       // rows = nodes, tiles of 128 nodes
@@ -803,16 +874,18 @@ __device__ __forceinline__ Tile make_tile(const SweepP& P, const StepTab& tb, in
   return T;
 }
 // one warp (lanes = segments); the caller publishes the table with a CTA-wide barrier
-__device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg_max, int G) {
+__device__ __noinline__ void build_step_table(const SweepP& P, StepTab& tb, int s, int L, int nseg_max, int G) {
   const int tid = threadIdx.x & 31;
   const int nseg = (s < 0) ? P.dirs : nseg_max;
   if (tid < kMaxSeg) {
-    Seg g = {0, 0, 0, 0};
+    Seg g = {0, 0, 0, 0, 0, 1, 0u};
     int gp = 0, gnn = 0;
     if (tid < nseg) {
       if (s < 0) g.n = P.N;
       else {
-        const int d = tid / P.layers, i = tid - d * P.layers, l = s - i;
+        int d, i;
+        seg_di(P, tid, d, i);
+        const int l = s - i;
         if (l >= 0 && l < L) {
           gp = P.dir[d].lvl_off[l];
           gnn = max(0, P.dir[d].lvl_off[l + 1] - gp);
@@ -827,17 +900,64 @@ __device__ __forceinline__ void build_step_table(const SweepP& P, StepTab& tb, i
   __syncwarp();
   if (tid == 0) {
     int t64 = 0;                                        // work in units of 128 rows x 64 columns
-    for (int q = 0; q < nseg; ++q) t64 += ceil_div(tb.seg[q].n, 128) * seg_blocks(P, s, q);
+    for (int q = 0; q < nseg; ++q) t64 += ((tb.seg[q].n + 127) >> 7) * seg_blocks(P, s, q);
     const int nbc = (t64 >= 4 * G) ? 4 : (t64 >= 2 * G) ? 2 : 1;
     const int nst = (nbc == 4 && t64 >= 8 * G) ? 2 : 1;
-    int base_ = 0;
+    int base_ = 0, bmod = 0;
+    const int rsh = 6 + nst, rmask = (64 << nst) - 1;   // rows per tile = 128 nst (nst = 1, 2)
+#pragma unroll 1
     for (int q = 0; q < kMaxSeg; ++q) {
-      tb.seg[q].ntile = (q < nseg) ? ceil_div(tb.seg[q].n, 128 * nst) * ceil_div(seg_blocks(P, s, q), nbc) : 0;
+      const int ncbt = (q < nseg) ? (seg_blocks(P, s, q) + nbc - 1) >> blk_shift(nbc) : 1;
+      tb.seg[q].ntile = (q < nseg) ? ((tb.seg[q].n + rmask) >> rsh) * ncbt : 0;
       tb.seg[q].base = base_;
+      tb.seg[q].bmod = bmod;
+      tb.seg[q].ncbt = ncbt;
+      tb.seg[q].rcbt = 0xffffffffu / (uint32_t)ncbt + 1u;       // ncbt == 1 wraps to 0: make_tile does not divide then
       base_ += tb.seg[q].ntile;
+      bmod = (bmod + tb.seg[q].ntile) % G;
     }
     tb.nbc = nbc; tb.nst = nst;
   }
+  __syncwarp();
+}
+
+// one warp, after build_step_table: list the nodes of step s with long in-edge lists (row pointers are constants too).
+// Every CTA derives the same list, so the split of the gate phase below needs no communication. Eight blocks of 32 row
+// pointers are in flight at a time: the scan has to hide behind the gate phase of the step before.
+__device__ __noinline__ void scan_heavy(const SweepP& P, const StepTab& tb, HeavyTab& hv, int s, int nseg) {
+  const int lane = threadIdx.x & 31;
+  int total = 0;
+  for (int q = 0; q < nseg; ++q) total += tb.gn[q];
+  int cnt = 0;
+  if (s < 0 || total > kScanRows) cnt = -1;
+  for (int q = 0; q < nseg && cnt >= 0; ++q) {
+    int d, i;
+    seg_di(P, q, d, i);
+    const int l = s - i;
+    const int n = tb.gn[q], pos0 = tb.gpos0[q];
+    if (n <= 0 || l <= 0) continue;                     // level 0 ignores its in-edges
+    const int* __restrict__ rp = P.dir[d].rowptr + pos0;
+    for (int r0 = 0; r0 < n && cnt >= 0; r0 += 256) {
+      int deg[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = r0 + 32 * k + lane;
+        deg[k] = (r < n) ? rp[r + 1] - rp[r] : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool h = deg[k] > kCoopEdges;
+        const unsigned m = __ballot_sync(0xffffffffu, h);
+        if (m && cnt >= 0) {
+          const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+          if (h && slot < kMaxHeavy) { hv.node[slot][0] = q; hv.node[slot][1] = pos0 + r0 + 32 * k + lane; }
+          cnt += __popc(m);
+          if (cnt > kMaxHeavy) cnt = -1;
+        }
+      }
+    }
+  }
+  if (lane == 0) hv.n = cnt;
   __syncwarp();
 }
 
@@ -879,6 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   if (nsteps > 0 && warp == kBuilderWarps) {
     build_step_table(P, S.tab[1], -1, L, nseg, G);
     build_step_table(P, S.tab[0], 0, L, nseg, G);
+    scan_heavy(P, S.tab[0], S.heavy[0], 0, nseg);
   }
   __syncthreads();
 
@@ -889,21 +1010,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
     if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; tr[8] = tr[9] = 0; }
     if (s >= 0) {
       // ---------------- gate phase of step s ----------------
-      const int W = G * kBuilderWarps;
       if (warp < kBuilderWarps) {
+        const StepTab& tg = S.tab[s & 1];
         if (tid == 0) S.ncoop = 0;
         builders_sync();
         int rbase = 0;
+#ifdef DAGNN_GATE_TRACE
+        bool gt_done = false;
+        if (tr && tid == 0) tr[10] = tr[11] = tr[12] = tr[13] = tr[14] = tr[15] = 0;
+#endif
+        // nodes with long in-edge lists, found one phase ahead: CTA h takes the h-th one, all warps, first thing; while
+        // they are few the ordinary rows go to the other CTAs only, so that no CTA does both and the phase is as long as
+        // one node, not two
+        const HeavyTab& hv = S.heavy[s & 1];
+        const int nh = hv.n;
+        int Gn = G, rank_n = rank;
+        if (nh > 0 && nh <= G / 2) { Gn = G - nh; rank_n = rank - nh; }
+        for (int h = rank; h < nh; h += G) {
+          const int q = hv.node[h][0], p = hv.node[h][1];
+          int d, i;
+          seg_di(P, q, d, i);
+#if defined(DAGNN_GATE_TRACE) && DAGNN_GATE_TRACE == 2
+          gate_node_cta(P, P.dir[d], P.lay[d][i], p, tg.gpos0[q], s - i, reinterpret_cast<float*>(As), warp, lane,
+                           (tr && tid == 0 && h == rank) ? tr : nullptr);
+#elif defined(DAGNN_GATE_TRACE)
+          gate_node_cta(P, P.dir[d], P.lay[d][i], p, tg.gpos0[q], s - i, reinterpret_cast<float*>(As), warp, lane, nullptr);
+#else
+          gate_node_cta(P, P.dir[d], P.lay[d][i], p, tg.gpos0[q], s - i, reinterpret_cast<float*>(As), warp, lane);
+#endif
+        }
+        const int W = Gn * kBuilderWarps;
         for (int q = 0; q < nseg; ++q) {
-          const int d = q / P.layers, i = q - d * P.layers, l = s - i;
-          const int pos0 = S.tab[s & 1].gpos0[q], n = S.tab[s & 1].gn[q];     // level offsets: table built one phase ahead
+          int d, i;
+          seg_di(P, q, d, i);
+          const int l = s - i;
+          const int pos0 = tg.gpos0[q], n = tg.gn[q];     // level offsets: table built one phase ahead
           if (n <= 0) continue;
           const DirP& D = P.dir[d];
-          // rows of the step are dealt to the warps of the grid, CTA-minor, continuing across segments
-          int r = ((warp * G + rank) - rbase % W + W) % W;
+          // rows of the step are dealt to the warps of the (remaining) CTAs, CTA-minor, continuing across segments
+          int r = warp * Gn + rank_n - rbase;           // rbase = rows dealt so far, mod W
+          if (r < 0) r += W;
+          if (rank_n < 0) r = n;
           for (; r < n; r += W) {
             const int p = pos0 + r;
             if (l > 0 && D.rowptr[p + 1] - D.rowptr[p] > kCoopEdges) {     // long in-edge list: leave it to the whole CTA
+              if (nh >= 0) continue;                                        // ... done above
               int slot = 0;
               if (lane == 0) slot = atomicAdd(&S.ncoop, 1);
               slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -912,20 +1063,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
                 continue;
               }
             }
+#ifdef DAGNN_GATE_TRACE
+#if DAGNN_GATE_TRACE == 3      // a node with 8..kCoopEdges in-edges, any warp
+            long long* gt = (tr && lane == 0 && l > 0 && D.rowptr[p + 1] - D.rowptr[p] >= 8) ? tr : nullptr;
+#elif DAGNN_GATE_TRACE == 2    // cooperative nodes only
+            long long* gt = nullptr;
+#else                          // the first node of warp 0
+            long long* gt = (tr && tid == 0 && !gt_done) ? tr : nullptr;
+#endif
+            if (gt) { gt[10] = clock64(); gt_done = true; }
+            gate_row<J>(P, D, P.lay[d][i], p, pos0, l, lane, gt);
+#else
             gate_row<J>(P, D, P.lay[d][i], p, pos0, l, lane);
+#endif
           }
           rbase += n;
+          if (rbase >= W) { rbase -= W; if (rbase >= W) rbase %= W; }
         }
         builders_sync();
-        const int nc = min(S.ncoop, kMaxCoop);
+        const int nc = min(S.ncoop, kMaxCoop);              // big steps: the nodes found while dealing the rows
         for (int c = 0; c < nc; ++c) {
           const int q = S.coop[c][0], p = S.coop[c][1];
-          const int d = q / P.layers, i = q - d * P.layers;
-          const int pos0 = S.tab[s & 1].gpos0[q];
-          gate_row_coop<J>(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
+          int d, i;
+          seg_di(P, q, d, i);
+          const int pos0 = tg.gpos0[q];
+#if defined(DAGNN_GATE_TRACE)
+          gate_node_cta(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane, nullptr);
+#else
+          gate_node_cta(P, P.dir[d], P.lay[d][i], p, pos0, s - i, reinterpret_cast<float*>(As), warp, lane);
+#endif
         }
       }
-      else if (s + 1 < nsteps) build_step_table(P, S.tab[(s + 1) & 1], s + 1, L, nseg, G);
+      else if (s + 1 < nsteps) {
+        build_step_table(P, S.tab[(s + 1) & 1], s + 1, L, nseg, G);
+        scan_heavy(P, S.tab[(s + 1) & 1], S.heavy[(s + 1) & 1], s + 1, nseg);
+      }
       if (tr && tid == 0) tr[8] = clock64();
       if (s + 1 < nsteps) grid_barrier(P.bar, ++nbar * (unsigned int)G);   // the last step's projection is empty
       if (tr && tid == 0) tr[9] = clock64();

@@ -138,14 +138,19 @@ int dagnn_pack_params_f32(const float* weight_ih, const float* weight_hh, const 
  *   inp_v = GRUCell_{d,i}(inp_v, m_v);  H[d][i][v] = inp_v          (inp_v starts as X[v])
  * replaces dagnn.py:144-182 incl. AttnConv (:362-373), PyG propagate/softmax/scatter-add, nn.GRUCell (:181) and
  * the index_put at :182; D-VAE variants dvae/dagnn.py:109-145, dvae/dagnn_bn.py:108-136.
- * ONE persistent cooperative kernel runs the whole sweep: wavefront step s = level + layer processes all (d, layer)
- * pairs of the step as tiles of <= 256 level rows x 16 or 64 hidden units dealt to one CTA per SM, with one grid
- * barrier between steps. Per tile: softmax weights of the rows' in-edges from per-node partial key scores, the
- * operand rows [inp_v | m_v] gathered straight into swizzled shared memory as fp16 hi/lo tiles, the gate GEMM on
- * tcgen05 (fp16 x 3 split, fp32 accumulators in TMEM), GRU pointwise epilogue out of TMEM. Level offsets and the
- * level count (reference: max level of direction 0, + 1 — dagnn.py:137) are read from the schedule's DEVICE arrays,
- * so a forward needs no host synchronisation. If sched->summary[2] != 0 (bad input) the kernel does nothing; the
- * caller checks the status. States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
+ * ONE persistent cooperative kernel (one CTA per SM) runs the whole sweep. Since W_hh (sum_e a_e h_e) = sum_e a_e (W_hh h_e),
+ * every node is projected ONCE, right after its state is final: P^i = W_hh^i h^i and Gi^{i+1} = W_ih^{i+1} h^i (one
+ * weight image [W_hh ; W_ih next]), Gi^0 = W_ih^0 X. Wavefront step s = level + layer handles all (d, layer) pairs of
+ * the step in two phases separated by grid barriers:
+ *   gate phase  one warp per node (the whole CTA for long in-edge lists): softmax over the in-edges from per-node scalar
+ *               key scores, weighted sum of the predecessors' P and h rows, GRU pointwise with the node's own Gi row;
+ *               the new state is stored as fp32 and as fp16 hi/lo halves in the tcgen05 operand-image layout;
+ *   proj phase  the rows the gate phase produced (contiguous: positions are level-sorted) x the weight image as
+ *               128/256-row tiles: operand and weight tiles arrive by bulk copy (cp.async.bulk + mbarrier), the GEMM
+ *               runs on tcgen05 (fp16 x 3 split, fp32 accumulators in TMEM), the epilogue stores P / Gi rows.
+ * Level offsets and the level count (reference: max level of direction 0, + 1 — dagnn.py:137) are read from the
+ * schedule's DEVICE arrays, so a forward needs no host synchronisation. If sched->summary[2] != 0 (bad input) the
+ * kernel does nothing; the caller checks the status. States are stored in POSITION order: H[d][i] is fp32 [N, ldh], row p = node perm[d][p].
  * Inputs must satisfy |x| < 65504 (fp16 range of the hi part); states are in (-1, 1) by construction.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct DagnnSweepArgs {
@@ -161,12 +166,13 @@ typedef struct DagnnSweepArgs {
   int32_t use_edge_attr;               /* 1: add the edge-type score term (sched->eattr must exist) */
   void* workspace;                     /* device scratch, dagnn_sweep_workspace_bytes(), 256-byte aligned */
   size_t workspace_bytes;
-  void* trace;                         /* optional profiling buffer (NULL = off): int64 [steps][grid<=256][16] clock64 values:
-                                          0 step begin, 1 first tile: operands built, 2 first tile: accumulators ready,
-                                          3 first tile stored, 4 all tiles done, 5 barrier passed, 6 #tiles of this CTA,
-                                          7 units per tile | rows per tile << 8; first tile, builder thread 0, cycles spent
-                                          in 8 pre-phase, 9 waiting for a free operand stage, 10 building, 11 hand-over;
-                                          issuer: 12 waiting for weights, 13 waiting for operands, 14 issuing, 15 #stages  */
+  void* trace;                         /* optional profiling buffer (NULL = off), dagnn_sweep_trace_bytes(steps):
+                                          int64 [steps + 1][256][16] clock64 values per (phase pair, CTA): entry k = proj
+                                          phase of the input (k = 0) or gate + proj phase of step k - 1. Slots: 0 begin,
+                                          8 gate phase done, 9 grid barrier passed, 1 first tile: operands ready,
+                                          2 first tile: accumulators ready, 3 first tile stored, 4 all tiles done,
+                                          5 second grid barrier passed, 6 #tiles of this CTA, 7 columns | rows << 12 of a
+                                          tile; 10..15 gate-phase stage stamps (builds with -DDAGNN_GATE_TRACE only)  */
 } DagnnSweepArgs;
 
 size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E, int32_t max_levels);
