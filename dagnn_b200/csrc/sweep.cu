@@ -711,7 +711,7 @@ __device__ __forceinline__ void ring_set_geometry(int nbc, SmemTail& S, RingStat
   R.nbc = nbc;
 }
 // weight chunk c of a tile -> next ring stage: hi tiles of the tile's blocks, then their lo tiles
-__device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigned char* Bs, SmemTail& S, RingState& R) {
+__device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigned char* Bs, SmemTail& S, RingState& R, bool leader) {
   const uint32_t nbs = 8u >> blk_shift(nbc);
   const uint32_t s = R.next;
   R.next = (s + 1 == nbs) ? 0u : s + 1;
@@ -720,6 +720,7 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
     R.empty_par ^= 1u << s;
     R.pending &= ~(1u << s);
   }
+  if (!leader) return;
   mbar_expect_tx(&S.b_full[s], (uint32_t)T.ncb * kBlkBytes);
   unsigned char* stg = Bs + (size_t)s * nbc * kBlkBytes;
   const unsigned char* img = reinterpret_cast<const unsigned char*>(T.img);
@@ -730,16 +731,22 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
   }
 }
 
+// Run by the WHOLE issuer warp, converged: every lane keeps the same ring state and waits on the same barriers, lane 0
+// (`leader`) alone starts copies, MMAs and commits. The operands of tcgen05.mma live in uniform registers; values the
+// compiler cannot prove warp-uniform (anything derived from the shared-memory step table) pass through uni() first,
+// otherwise every MMA is wrapped in a ~100-cycle elect / broadcast loop and a 64-column tile is issue-bound.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
-                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc) {
+                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc,
+                                            bool leader) {
   const int nbs = 8 >> blk_shift(nbc);
-  const uint32_t idesc = tc::instr_desc_f16(128, 64 * T.ncb);
+  const uint32_t idesc = uni(tc::instr_desc_f16(128, 64 * T.ncb));
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
   // was still computing, or before a grid barrier)
   if (R.pre == 0) ring_set_geometry(nbc, S, R);
   const uint32_t first = R.pre ? R.pre_first : R.next;
   const int npre = min(nbs, T.nck);
-  for (int c = (int)R.pre; c < npre; ++c) ring_load(T, nbc, c, Bs, S, R);
+  for (int c = (int)R.pre; c < npre; ++c) ring_load(T, nbc, c, Bs, S, R, leader);
   R.pre = 0;
   // operand side when the tiles come ready-made: item it = (chunk c, sub-tile st) -> stage (ja + it) % kNAS, two bulk copies
   // (hi, lo) of the rows the sub-tile really has, rounded up to the 8-row swizzle group
@@ -749,6 +756,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
     const uint32_t j = ja + (uint32_t)it;
     const uint32_t stage = j % kNAS, use = j / kNAS;
     if (use >= 1) mbar_wait(&S.a_empty[stage], (use - 1) & 1u);        // MMAs that read this stage are done
+    if (!leader) return;
     const uint32_t bytes = (uint32_t)((min(128, T.nrows - st * 128) + 7) & ~7) * tc::ROW_BYTES;
     const unsigned char* src = T.aimg + ((size_t)st * T.nck + c) * kAStageBytes;
     unsigned char* dst = As + (size_t)stage * kAStageBytes;
@@ -758,7 +766,7 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   };
   const uint32_t sbytes = 2u * (uint32_t)T.small * tc::ROW_BYTES;      // compact stage: hi + lo tile of T.small rows
   if (T.small) {
-    for (int c = 0; c < T.nck; ++c) {
+    for (int c = 0; c < (leader ? T.nck : 0); ++c) {
       const unsigned char* src = T.aimg + (size_t)c * kAStageBytes;
       unsigned char* dst = As + (size_t)c * sbytes;
       mbar_expect_tx(&S.c_full[c], sbytes);
@@ -773,8 +781,8 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
     const uint32_t s = (first + (uint32_t)c) & (uint32_t)(nbs - 1);
     mbar_wait(&S.b_full[s], R.full_par >> s & 1u);
     R.full_par ^= 1u << s;
-    const uint32_t sb = smem_u32(Bs + (size_t)s * nbc * kBlkBytes);
-    const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)nbc * (kBlkBytes / 2));
+    const uint32_t sb = uni(smem_u32(Bs + (size_t)s * nbc * kBlkBytes));
+    const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + uni((uint32_t)nbc * (kBlkBytes / 2)));
 #pragma unroll 1
     for (int st = 0; st < T.nst; ++st) {
       const uint32_t j = ja + (uint32_t)(c * T.nst + st);
@@ -783,29 +791,30 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
       else mbar_wait(&S.a_full[stage], use & 1u);
       if (c == 0 && st == 0 && ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);   // operand tiles arrive by bulk copy: nothing
       tc::fence_after_sync();                                                      // else orders us behind the epilogue
-      const uint32_t sa = T.small ? smem_u32(As + (size_t)c * sbytes) : smem_u32(As + (size_t)stage * kAStageBytes);
-      const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + (T.small ? sbytes / 2 : 128 * tc::ROW_BYTES));
-      const uint32_t tm = tmem + (uint32_t)(st * 64 * nbc);
+      const uint32_t sa = uni(T.small ? smem_u32(As + (size_t)c * sbytes) : smem_u32(As + (size_t)stage * kAStageBytes));
+      const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + uni(T.small ? sbytes / 2 : 128 * tc::ROW_BYTES));
+      const uint32_t tm = uni(tmem + (uint32_t)(st * 64 * nbc));
+      const bool fresh = uni(c == 0 ? 1u : 0u) != 0;
+      if (leader) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, c == 0 && ks == 0);
-      if (!T.small) {
-        tc::commit(&S.a_empty[stage]);
-        if (T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
+        for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, fresh && ks == 0);
+        if (!T.small) tc::commit(&S.a_empty[stage]);
       }
+      if (!T.small && T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
     }
-    tc::commit(&S.b_empty[s]);
+    if (leader) tc::commit(&S.b_empty[s]);
     R.pending |= 1u << s;
     // refill: chunk c + nbs - 1 goes where chunk c - 1 was (its MMAs precede the ones just issued)
-    if (c >= 1 && c + nbs - 1 < T.nck) ring_load(T, nbc, c + nbs - 1, Bs, S, R);
+    if (c >= 1 && c + nbs - 1 < T.nck) ring_load(T, nbc, c + nbs - 1, Bs, S, R, leader);
   }
-  tc::commit(&S.acc_full);
+  if (leader) tc::commit(&S.acc_full);
   // weights are constants: put the first chunks of this CTA's NEXT tile in flight now — they land while the current
   // accumulators drain, the epilogue runs and (for the first tile of the next proj phase) the gate phase runs
   if (nextT) {
     ring_set_geometry(next_nbc, S, R);
     R.pre_first = R.next;
     const int n2 = min(8 >> blk_shift(next_nbc), nextT->nck);
-    for (int c = 0; c < n2; ++c) ring_load(*nextT, next_nbc, c, Bs, S, R);
+    for (int c = 0; c < n2; ++c) ring_load(*nextT, next_nbc, c, Bs, S, R, leader);
     R.pre = (uint32_t)n2;
   }
 }
@@ -1118,7 +1127,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
       more = tile_advance(tb, nseg_now, rank, G, it);
       if (warp < kBuilderWarps) {
         builder_tile(P, T, As, S, tmem, ja, ct, 64 * tb.nbc, my_tiles == 0 ? tr : nullptr);
-      } else if (lane == 0) {
+      } else {                                       // the issuer warp, all lanes (see issuer_tile)
         Tile N;
         int nn = tb.nbc;
         bool hn = more;
@@ -1128,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           hn = tile_advance(tbn, nseg, rank, G, it2);
           if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
         }
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn, lane == 0);
       }
       __syncwarp();
       if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier
