@@ -736,9 +736,18 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
 // compiler cannot prove warp-uniform (anything derived from the shared-memory step table) pass through uni() first,
 // otherwise every MMA is wrapped in a ~100-cycle elect / broadcast loop and a 64-column tile is issue-bound.
 __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// one lane of the converged warp (always the same one). Guarding the single-thread instructions with elect.sync rather
+// than lane == 0 lets ptxas drop its own elect loop around every tcgen05.mma (65 -> 42 cycles per issue, tools/ubench_mma.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
                                             uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc,
-                                            bool leader) {
+                                            bool leader, long long* tr) {
+  const bool trc = tr != nullptr && leader;            // stamps of the first tile of a phase: 10 start, 11 first operands there,
+  if (trc) tr[10] = clock64();                         // 13 / 14 chunk 0 / 1 issued, 12 everything issued
   const int nbs = 8 >> blk_shift(nbc);
   const uint32_t idesc = uni(tc::instr_desc_f16(128, 64 * T.ncb));
   // chunk c sits in stage (first + c) % nbs; the first chunks may already be in flight (issued while the previous tile
@@ -791,23 +800,26 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
       else mbar_wait(&S.a_full[stage], use & 1u);
       if (c == 0 && st == 0 && ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);   // operand tiles arrive by bulk copy: nothing
       tc::fence_after_sync();                                                      // else orders us behind the epilogue
+      if (trc && c == 0 && st == 0) tr[11] = clock64();
       const uint32_t sa = uni(T.small ? smem_u32(As + (size_t)c * sbytes) : smem_u32(As + (size_t)stage * kAStageBytes));
       const uint64_t ah = tc::smem_desc(sa), al = tc::smem_desc(sa + uni(T.small ? sbytes / 2 : 128 * tc::ROW_BYTES));
       const uint32_t tm = uni(tmem + (uint32_t)(st * 64 * nbc));
       const bool fresh = uni(c == 0 ? 1u : 0u) != 0;
-      if (leader) {
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tm, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, fresh && ks == 0);
         if (!T.small) tc::commit(&S.a_empty[stage]);
       }
       if (!T.small && T.aimg && c * T.nst + st + kNAS < nitems) load_A(c * T.nst + st + kNAS);   // refill this stage once its MMAs are done
     }
-    if (leader) tc::commit(&S.b_empty[s]);
+    if (elect_one()) tc::commit(&S.b_empty[s]);
+    if (trc && c < 2) tr[13 + c] = clock64();
     R.pending |= 1u << s;
     // refill: chunk c + nbs - 1 goes where chunk c - 1 was (its MMAs precede the ones just issued)
     if (c >= 1 && c + nbs - 1 < T.nck) ring_load(T, nbc, c + nbs - 1, Bs, S, R, leader);
   }
-  if (leader) tc::commit(&S.acc_full);
+  if (trc) tr[12] = clock64();
+  if (elect_one()) tc::commit(&S.acc_full);
   // weights are constants: put the first chunks of this CTA's NEXT tile in flight now — they land while the current
   // accumulators drain, the epilogue runs and (for the first tile of the next proj phase) the gate phase runs
   if (nextT) {
@@ -1137,7 +1149,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
           hn = tile_advance(tbn, nseg, rank, G, it2);
           if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
         }
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn, lane == 0);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn, lane == 0, my_tiles == 0 ? tr : nullptr);
       }
       __syncwarp();
       if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier

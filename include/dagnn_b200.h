@@ -172,7 +172,9 @@ typedef struct DagnnSweepArgs {
                                           8 gate phase done, 9 grid barrier passed, 1 first tile: operands ready,
                                           2 first tile: accumulators ready, 3 first tile stored, 4 all tiles done,
                                           5 second grid barrier passed, 6 #tiles of this CTA, 7 columns | rows << 12 of a
-                                          tile; 10..15 gate-phase stage stamps (builds with -DDAGNN_GATE_TRACE only)  */
+                                          tile; issuer warp, first tile: 10 start, 11 first operands landed, 13 / 14 chunk 0 / 1
+                                          issued, 12 all MMAs issued (10..15 are gate-phase stage stamps instead in builds
+                                          with -DDAGNN_GATE_TRACE)  */
 } DagnnSweepArgs;
 
 size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int32_t Din, int32_t H, int64_t N, int64_t E, int32_t max_levels);

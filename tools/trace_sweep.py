@@ -26,7 +26,7 @@ tr = tr.cpu().numpy()[:, :148, :].astype(np.float64)
 MHZ = 1965.0
 lo = sched.lvl_off_host
 print("all times in us, max over CTAs unless noted. row s = gate phase of step s, then projection of the rows it produced (row -1: X)")
-print("step | level sizes | gate(max) gate(med) bar1 | cols rows tiles/CTA | build  acc  epi  rest | bar2(min) | step")
+print("step | level sizes | gate(max) gate(med) bar1 | cols rows tiles/CTA | build  acc  epi  rest | bar2(min) | step | issuer, first tile: start->operands->MMAs issued->acc seen")
 tot = 0
 for k in range(steps + 1):
     s = k - 1
@@ -43,7 +43,12 @@ for k in range(steps + 1):
     stepdur = ((end - t[:, 0]) / MHZ).max()
     tot += stepdur
     f = int(t[0, 7])
+    i0 = np.where(act, (t[:, 10] - p0) / MHZ, 0); i1 = np.where(act, (t[:, 11] - t[:, 10]) / MHZ, 0)
+    i2 = np.where(act, (t[:, 12] - t[:, 11]) / MHZ, 0); i3 = np.where(act, (t[:, 2] - t[:, 12]) / MHZ, 0)
+    i4 = np.where(act, (t[:, 13] - t[:, 11]) / MHZ, 0); i5 = np.where(act, (t[:, 14] - t[:, 13]) / MHZ, 0)
+    med = lambda x: np.median(x[act]) if act.any() else 0
+    iss = " | %4.1f %4.1f %4.1f %4.1f (chunk 0 %4.2f, chunk 1 %4.2f)" % (med(i0), med(i1), med(i2), med(i3), med(i4), med(i5))
     print("%3d | %12s | %6.1f %6.1f %5.1f | %3d %3d %2d | %6.1f %6.1f %6.1f %6.1f | %5.1f | %7.1f" % (
         s, n0, gate.max(), np.median(gate), bar1.min() if s >= 0 else 0, f & 4095, f >> 12, int(t[:, 6].max()), g.max(), bw.max(), pm.max(), tl.max(),
-        bar2.min(), stepdur))
+        bar2.min(), stepdur) + iss)
 print("sum of step durations: %.1f us" % tot)
