@@ -105,26 +105,24 @@ class Schedule(object):
         ws_bytes = lib().dagnn_schedule_workspace_bytes(N, E, ML)
         buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
         s.buf, s.head_len, s.max_levels = buf, head, ML
-        view = lambda k, n: buf[offs[k]: offs[k] + n]
+        # the C struct gets plain addresses (base + offset); the tensor views of the same ranges are only built when
+        # somebody asks for them (tests, tools) — a forward never does, and 15 slices cost more host time than the launch
+        s._offs, s._dims = offs, (N, E, B, dirs, ML, edge_attr is not None)
+        base = buf.data_ptr()
+        addr = lambda k: base + 4 * offs[k]
         c = s.c
         c.N, c.E, c.B, c.dirs, c.max_levels = N, E, B, dirs, ML
-        s.summary = view("head", 8)
-        c.summary = s.summary.data_ptr()
-        s.perm, s.pos, s.lvl_off, s.rowptr, s.col, s.eid, s.eattr = [], [], [], [], [], [], []
+        c.summary = addr("head")
         for d in range(dirs):
-            s.perm.append(view("perm%d" % d, N)); s.pos.append(view("pos%d" % d, N))
-            s.lvl_off.append(buf[offs["head"] + 8 + d * (ML + 1): offs["head"] + 8 + (d + 1) * (ML + 1)])
-            s.rowptr.append(view("rowptr%d" % d, N + 1)); s.col.append(view("col%d" % d, E)); s.eid.append(view("eid%d" % d, E))
-            s.eattr.append(view("eattr%d" % d, 2 * E).view(torch.float32).view(E, 2) if edge_attr is not None else None)
-            c.perm[d], c.pos[d], c.lvl_off[d] = s.perm[d].data_ptr(), s.pos[d].data_ptr(), s.lvl_off[d].data_ptr()
-            c.rowptr[d], c.col[d], c.eid[d] = s.rowptr[d].data_ptr(), s.col[d].data_ptr(), s.eid[d].data_ptr()
-            c.eattr[d] = s.eattr[d].data_ptr() if edge_attr is not None else None
-        s.gptr = view("gptr", B + 1)
-        c.gptr = s.gptr.data_ptr()
-        ws = buf[tot:]
+            c.perm[d], c.pos[d] = addr("perm%d" % d), addr("pos%d" % d)
+            c.lvl_off[d] = base + 4 * (offs["head"] + 8 + d * (ML + 1))
+            c.rowptr[d], c.col[d], c.eid[d] = addr("rowptr%d" % d), addr("col%d" % d), addr("eid%d" % d)
+            c.eattr[d] = addr("eattr%d" % d) if edge_attr is not None else None
+        c.gptr = addr("gptr")
+        ws_ptr = base + 4 * tot
         check(lib().dagnn_schedule_build(_ptr(edge_index), _ptr(levels[0]), _ptr(levels[1]) if dirs == 2 else None,
                                          _ptr(node_ids[0]), _ptr(node_ids[1]) if dirs == 2 else None,
-                                         _ptr(edge_attr), _ptr(batch), C.byref(c), ws.data_ptr(), ws_bytes, _stream()),
+                                         _ptr(edge_attr), _ptr(batch), C.byref(c), ws_ptr, ws_bytes, _stream()),
               "dagnn_schedule_build")
         s._keep = [edge_index, levels, node_ids, edge_attr, batch]
         s.has_edge_attr = edge_attr is not None
@@ -155,6 +153,51 @@ class Schedule(object):
                                   "longest-path levels of one DAG" % (self._num_levels[1], self._num_levels[0]))
         self._final = True
         return self
+
+    # ---- tensor views of the device arrays (built on demand)
+    def _view(self, key: str, n: int) -> torch.Tensor:
+        o = self._offs[key]
+        return self.buf[o: o + n]
+
+    @property
+    def summary(self) -> torch.Tensor:
+        return self._view("head", 8)
+
+    @property
+    def perm(self) -> List[torch.Tensor]:
+        return [self._view("perm%d" % d, self._dims[0]) for d in range(self._dims[3])]
+
+    @property
+    def pos(self) -> List[torch.Tensor]:
+        return [self._view("pos%d" % d, self._dims[0]) for d in range(self._dims[3])]
+
+    @property
+    def lvl_off(self) -> List[torch.Tensor]:
+        ML, h = self._dims[4], self._offs["head"]
+        return [self.buf[h + 8 + d * (ML + 1): h + 8 + (d + 1) * (ML + 1)] for d in range(self._dims[3])]
+
+    @property
+    def rowptr(self) -> List[torch.Tensor]:
+        return [self._view("rowptr%d" % d, self._dims[0] + 1) for d in range(self._dims[3])]
+
+    @property
+    def col(self) -> List[torch.Tensor]:
+        return [self._view("col%d" % d, self._dims[1]) for d in range(self._dims[3])]
+
+    @property
+    def eid(self) -> List[torch.Tensor]:
+        return [self._view("eid%d" % d, self._dims[1]) for d in range(self._dims[3])]
+
+    @property
+    def eattr(self) -> List[Optional[torch.Tensor]]:
+        E = self._dims[1]
+        if not self._dims[5]:
+            return [None] * self._dims[3]
+        return [self._view("eattr%d" % d, 2 * E).view(torch.float32).view(E, 2) for d in range(self._dims[3])]
+
+    @property
+    def gptr(self) -> torch.Tensor:
+        return self._view("gptr", self._dims[2] + 1)
 
     @property
     def num_levels(self) -> List[int]:
@@ -220,7 +263,7 @@ class PackedParams(object):
                 params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag.attn_lin.weight]
                 if use_edge_attr:
                     params.append(ag.edge_encoder.weight)
-        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (Din, H, nvid, use_edge_attr)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (Din, H, nvid, use_edge_attr, str(device))
         if key == self.key:
             return self
         self.blobs, self.layouts = [], []
@@ -278,9 +321,10 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
     ws = _sweep_workspace(X.device, dirs, num_layers, Din, H, N, sched.c.E, sched.c.max_levels)
     a = DagnnSweepArgs()
     a.sched = C.pointer(sched.c)
+    hs0, hs_stride = Hs.data_ptr(), N * ldh * 4
     for d in range(dirs):
         for i in range(num_layers):
-            a.Hs[d][i] = Hs[d, i].data_ptr()
+            a.Hs[d][i] = hs0 + (d * num_layers + i) * hs_stride
             a.packed[d][i] = packed.blobs[d][i].data_ptr()
     a.num_layers = num_layers
     a.Din, a.H, a.nvid = Din, H, nvid
