@@ -158,10 +158,10 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   asm volatile("fence.proxy.async;" ::: "memory");
   if (threadIdx.x < kBuilders) asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // release: the CTA's global stores (ordered before this thread by the named barrier) are visible at GPU scope before
+    // the arrival counts; no return value, so the first poll goes out right behind it instead of after a round trip
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     while (ld_acquire_u32(bar) < target) {}
-    __threadfence();
   }
   __syncthreads();
 }
