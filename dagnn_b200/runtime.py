@@ -18,7 +18,13 @@ POOLS = {"max": 0, "mean": 1, "add": 2}
 FILTER_ALL, FILTER_LVL0, FILTER_LAST, FILTER_FIRST = 0, 1, 2, 3
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the launching stream of every C-ABI call)."""
+    if _RAW_STREAM is not None:        # same value, a fraction of the host time of current_stream().cuda_stream
+        return _RAW_STREAM(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -48,13 +54,17 @@ def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, m
     X = torch.empty(N, D, device=x.device, dtype=torch.float32)
     img = None
     if D % 4 == 0:
-        img = torch.empty(int(lib().dagnn_operand_image_bytes(N, D)) + 1024, device=x.device, dtype=torch.uint8)
+        nb = int(lib().dagnn_operand_image_bytes(N, D))
+        img = torch.empty(nb + 1024, device=x.device, dtype=torch.uint8)
         off = (-img.data_ptr()) % 1024
-        img = img[off: off + int(lib().dagnn_operand_image_bytes(N, D))]
+        img = img[off: off + nb]
     check(lib().dagnn_embed_f32(_ptr(x), _ptr(depth), _ptr(T), _ptr(A), _ptr(P), int(max_depth), N, D, _ptr(X), D,
                                 _ptr(img), _stream()), "dagnn_embed_f32")
     X._dagnn_image = img
     return X
+
+
+_LAYOUTS = {}      # (N, E, B, dirs, max_levels, has edge attributes) -> (offsets, total, workspace bytes) of a schedule buffer
 
 
 class Schedule(object):
@@ -92,17 +102,23 @@ class Schedule(object):
         s = Schedule()
         ML = int(max_levels)
         head = 8 + dirs * (ML + 1)
-        sizes = [("head", head)]
-        for d in range(dirs):
-            sizes += [("perm%d" % d, N), ("pos%d" % d, N), ("rowptr%d" % d, N + 1), ("col%d" % d, E), ("eid%d" % d, E)]
-            if edge_attr is not None:
-                sizes.append(("eattr%d" % d, 2 * E))
-        sizes.append(("gptr", B + 1))
-        offs, tot = {}, 0
-        for k, n in sizes:
-            offs[k] = tot
-            tot += _align(max(n, 1))
-        ws_bytes = lib().dagnn_schedule_workspace_bytes(N, E, ML)
+        lkey = (N, E, B, dirs, ML, edge_attr is not None)
+        lay = _LAYOUTS.get(lkey)
+        if lay is None:
+            sizes = [("head", head)]
+            for d in range(dirs):
+                sizes += [("perm%d" % d, N), ("pos%d" % d, N), ("rowptr%d" % d, N + 1), ("col%d" % d, E), ("eid%d" % d, E)]
+                if edge_attr is not None:
+                    sizes.append(("eattr%d" % d, 2 * E))
+            sizes.append(("gptr", B + 1))
+            offs, tot = {}, 0
+            for k, n in sizes:
+                offs[k] = tot
+                tot += _align(max(n, 1))
+            if len(_LAYOUTS) > 64:
+                _LAYOUTS.clear()
+            lay = _LAYOUTS[lkey] = (offs, tot, int(lib().dagnn_schedule_workspace_bytes(N, E, ML)))
+        offs, tot, ws_bytes = lay
         buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
         s.buf, s.head_len, s.max_levels = buf, head, ML
         # the C struct gets plain addresses (base + offset); the tensor views of the same ranges are only built when
@@ -302,7 +318,7 @@ _WS = {}
 
 def _sweep_workspace(device, dirs, layers, Din, H, N, E, max_levels) -> torch.Tensor:
     need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H, N, E, max_levels))
-    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
+    key = (device.type, device.index, _stream())
     w = _WS.get(key)
     if w is None or w.numel() * 4 < need:
         w = torch.zeros((need + 3) // 4, device=device, dtype=torch.int32)
