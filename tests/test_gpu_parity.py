@@ -276,12 +276,15 @@ def _bipartite_batch(n_src, n_dst, seed):
                       _bi_layer_idx0=l0, _bi_layer_index0=ids.clone(), _bi_layer_idx1=l1, _bi_layer_index1=ids.clone(), num_graphs=1)
 
 
-@pytest.mark.parametrize("n_src,n_dst,hid", [(12, 7300, 32), (40, 300, 64), (3, 70, 520)])
+@pytest.mark.parametrize("n_src,n_dst,hid", [(12, 7300, 32), (40, 300, 64), (3, 70, 520), (14, 100, 64), (11, 200, 40),
+                                             (1500, 20, 32)])
 def test_long_in_edge_lists_and_wide_states(n_src, n_dst, hid, dev):
     """Gate-phase corner paths: in-edge lists longer than the per-warp limit (whole-CTA aggregation), longer than one
     32-edge round, more long lists in one CTA than its cooperative queue holds (7300 sinks with 12 in-edges each over 148
     CTAs: a warp then walks the list alone), lists of thousands of edges (reverse direction), and hidden states wider than
-    one 512-column pass."""
+    one 512-column pass. Small steps list their long in-edge lists a phase ahead and give each a CTA of its own: 40 such
+    nodes (the other CTAs take the ordinary rows), 100 (more than half the grid: everybody takes rows too), 200 (more than the
+    list holds: back to collecting them while dealing rows); 20 sinks fed by 1500 sources each in a step of 1520 rows."""
     from dagnn_b200 import data as D, ogb, runtime as rt
     from oracle import dagnn_oracle as O
     B = _bipartite_batch(n_src, n_dst, 5)
