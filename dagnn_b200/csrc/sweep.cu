@@ -744,8 +744,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
-                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, const Tile* nextT, int next_nbc,
-                                            bool leader, long long* tr) {
+                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, bool leader, long long* tr) {
   const bool trc = tr != nullptr && leader;            // stamps of the first tile of a phase: 10 start, 11 first operands there,
   if (trc) tr[10] = clock64();                         // 13 / 14 chunk 0 / 1 issued, 12 everything issued
   const int nbs = 8 >> blk_shift(nbc);
@@ -820,15 +819,16 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
   }
   if (trc) tr[12] = clock64();
   if (elect_one()) tc::commit(&S.acc_full);
-  // weights are constants: put the first chunks of this CTA's NEXT tile in flight now — they land while the current
-  // accumulators drain, the epilogue runs and (for the first tile of the next proj phase) the gate phase runs
-  if (nextT) {
-    ring_set_geometry(next_nbc, S, R);
-    R.pre_first = R.next;
-    const int n2 = min(8 >> blk_shift(next_nbc), nextT->nck);
-    for (int c = 0; c < n2; ++c) ring_load(*nextT, next_nbc, c, Bs, S, R, leader);
-    R.pre = (uint32_t)n2;
-  }
+}
+// weights are constants: put the first chunks of this CTA's NEXT tile in flight right after the current tile's MMAs are
+// queued — they land while the accumulators drain, the epilogue runs and (for the first tile of the next proj phase) the
+// gate phase runs. The next tile is worked out here, behind the MMAs, not in front of them.
+__device__ __forceinline__ void issuer_prefetch(const Tile& N, int next_nbc, unsigned char* Bs, SmemTail& S, RingState& R, bool leader) {
+  ring_set_geometry(next_nbc, S, R);
+  R.pre_first = R.next;
+  const int n2 = min(8 >> blk_shift(next_nbc), N.nck);
+  for (int c = 0; c < n2; ++c) ring_load(N, next_nbc, c, Bs, S, R, leader);
+  R.pre = (uint32_t)n2;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1140,16 +1140,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
       if (warp < kBuilderWarps) {
         builder_tile(P, T, As, S, tmem, ja, ct, 64 * tb.nbc, my_tiles == 0 ? tr : nullptr);
       } else {                                       // the issuer warp, all lanes (see issuer_tile)
-        Tile N;
-        int nn = tb.nbc;
-        bool hn = more;
-        if (more) N = make_tile(P, tb, s, it);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, lane == 0, my_tiles == 0 ? tr : nullptr);
+        if (more) issuer_prefetch(make_tile(P, tb, s, it), tb.nbc, Bs, S, R, lane == 0);
         else if (has_next) {
           TileIt it2 = {0, -1};
-          hn = tile_advance(tbn, nseg, rank, G, it2);
-          if (hn) { N = make_tile(P, tbn, s + 1, it2); nn = tbn.nbc; }
+          if (tile_advance(tbn, nseg, rank, G, it2)) issuer_prefetch(make_tile(P, tbn, s + 1, it2), tbn.nbc, Bs, S, R, lane == 0);
         }
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, hn ? &N : nullptr, nn, lane == 0, my_tiles == 0 ? tr : nullptr);
       }
       __syncwarp();
       if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier
