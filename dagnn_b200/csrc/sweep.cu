@@ -39,7 +39,7 @@ constexpr int kNBBar = 8;
 constexpr int kMaxSeg = DAGNN_MAX_DIRS * DAGNN_MAX_LAYERS;
 constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 columns
 constexpr int kMaxChunks = 16;                           // k chunks of a tile that may use compact operand stages
-constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (8 warps split the edge list)
+constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (split by columns)
 constexpr int kMaxCoop = 48;       // ... per CTA and gate phase; beyond that a warp does the node alone
 constexpr int kScanRows = 2048;    // steps with at most this many rows are latency-bound: their long in-edge lists are found a
 constexpr int kMaxHeavy = 128;     // phase ahead (at most this many) and get a CTA of their own, from the start of the phase
@@ -744,7 +744,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
-                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, bool leader, long long* tr) {
+                                            uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, bool leader, bool prev_small,
+                                            long long* tr) {
   const bool trc = tr != nullptr && leader;            // stamps of the first tile of a phase: 10 start, 11 first operands there,
   if (trc) tr[10] = clock64();                         // 13 / 14 chunk 0 / 1 issued, 12 everything issued
   const int nbs = 8 >> blk_shift(nbc);
@@ -773,6 +774,10 @@ __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned cha
     bulk_g2s(dst + 128 * tc::ROW_BYTES, src + 128 * tc::ROW_BYTES, bytes, &S.a_full[stage]);
   };
   const uint32_t sbytes = 2u * (uint32_t)T.small * tc::ROW_BYTES;      // compact stage: hi + lo tile of T.small rows
+  // The compact stages of a small tile share the operand region with the ring but are not part of it (no a_empty hand-over):
+  // when this tile or the one before it is small, the previous tile's MMAs — possibly still reading the region — must be
+  // done before anything is copied over it. (Across phases that barrier completed long ago.)
+  if (ct >= 1 && (T.small || prev_small)) mbar_wait(&S.acc_full, (ct - 1) & 1u);
   if (T.small) {
     for (int c = 0; c < (leader ? T.nck : 0); ++c) {
       const unsigned char* src = T.aimg + (size_t)c * kAStageBytes;
@@ -1012,6 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   const int nsteps = ok ? L + P.layers - 1 : 0;
   const int nseg = P.dirs * P.layers;
   const int G = (int)gridDim.x, rank = (int)blockIdx.x;
+  bool prev_small = false;                     // the CTA's previous projection tile used the compact operand stages
   uint32_t ja = 0, ct = 0, cs = 0;             // operand-ring items and tiles processed so far, phase bits of the chunk barriers
   RingState R = {0u, 0u, 0u, 0u, 0u, 0u, 0};
   unsigned int nbar = 0;
@@ -1140,7 +1146,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
       if (warp < kBuilderWarps) {
         builder_tile(P, T, As, S, tmem, ja, ct, 64 * tb.nbc, my_tiles == 0 ? tr : nullptr);
       } else {                                       // the issuer warp, all lanes (see issuer_tile)
-        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, lane == 0, my_tiles == 0 ? tr : nullptr);
+        issuer_tile(T, tb.nbc, As, Bs, S, tmem, ja, cs, ct, R, lane == 0, prev_small, my_tiles == 0 ? tr : nullptr);
         if (more) issuer_prefetch(make_tile(P, tb, s, it), tb.nbc, Bs, S, R, lane == 0);
         else if (has_next) {
           TileIt it2 = {0, -1};
@@ -1150,6 +1156,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
       __syncwarp();
       if (T.small) cs ^= (1u << T.nck) - 1u;         // tiles differ in their number of chunks: one phase bit per chunk barrier
       else ja += (uint32_t)(T.nck * T.nst);
+      prev_small = T.small != 0;
       ct += 1;
       ++my_tiles;
     }
