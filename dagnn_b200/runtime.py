@@ -64,6 +64,35 @@ def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, m
     return X
 
 
+def dag_levels(edge_index: torch.Tensor, num_nodes: int, max_passes: int = 257):
+    """Longest-path levels of a batch of DAGs on the device: (levels on the edges as given, levels on the reversed edges),
+    int64 [N] each — `_bi_layer_idx0`, `_bi_layer_idx1` of the reference (`top_sort` / `add_order_info_01`,
+    src/utils_dag.py:8-35,39-52; the node-id rows `_bi_layer_index0/1` are arange(N)). OGB: pass the AST edges only.
+    One D2H of the 4-int summary at the end; a batch deeper than max_passes - 1 levels is retried with more passes,
+    an edge list that is still moving after N + 1 passes is not acyclic (ValueError, like the host version)."""
+    edge_index = _req_cuda(edge_index, "edge_index", torch.int64)
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise _lib.DagnnError("edge_index must be [2, E]")
+    edge_index = edge_index.contiguous()
+    N, E, dev = int(num_nodes), int(edge_index.shape[1]), edge_index.device
+    passes = max(1, int(max_passes))
+    while True:
+        ws = torch.empty((int(lib().dagnn_levels_workspace_bytes(N, passes)) + 3) // 4, device=dev, dtype=torch.int32)
+        lf = torch.empty(N, device=dev, dtype=torch.int64)
+        lb = torch.empty(N, device=dev, dtype=torch.int64)
+        summary = torch.empty(4, device=dev, dtype=torch.int32)
+        check(lib().dagnn_levels_build(_ptr(edge_index), N, E, passes, _ptr(lf), _ptr(lb), _ptr(summary), _ptr(ws),
+                                       ws.numel() * 4, _stream()), "dagnn_levels_build")
+        status = int(summary[1].item())
+        if status == 0:
+            return lf, lb
+        if status == 2:
+            raise _lib.DagnnError("dag_levels: an edge endpoint is outside [0, %d)" % N)
+        if passes > N + 1:
+            raise ValueError("edge list is not acyclic")
+        passes = min(passes * 8, N + 2)
+
+
 _LAYOUTS = {}      # (N, E, B, dirs, max_levels, has edge attributes) -> (offsets, total, workspace bytes) of a schedule buffer
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 5
+#define DAGNN_ABI_VERSION 6
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -95,6 +95,22 @@ size_t dagnn_schedule_workspace_bytes(int64_t N, int64_t E, int32_t max_levels);
 int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const int64_t* lvl1,
                          const int64_t* nid0, const int64_t* nid1, const float* edge_attr, const int64_t* batch,
                          const DagnnSchedule* sched, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Input side: longest-path level of every node of a batch of DAGs, on the edges as given
+ * (lvl_fwd) and on the reversed edges (lvl_bwd) — what the reference computes per graph on the host when a data set is
+ * built and stores as `_bi_layer_idx0/1` / `bi_layer_index[d][0]`: `top_sort` src/utils_dag.py:8-35,
+ * `add_order_info_01` :39-52, `add_order_info` :70-76 (the node-id rows are arange(N)). OGB: pass the raw AST edges,
+ * not the augmented ones (ogb/io/read_graph_pyg.py:51 runs before augment_edge2).
+ * edge_index int64 [2, E] (row 0 sources, row 1 targets), outputs int64 [N]. Bit-exact (integers).
+ * summary: device int32 [4], written by the call: [0] number of levels (max lvl_fwd + 1), [1] status — 0 ok, 1 not at the
+ * fixed point after max_passes passes over the edges (batch deeper than max_passes - 1, or a cycle: call again with
+ * more passes; more than N passes means the edge list is not acyclic), 2 an edge endpoint outside [0, N) —,
+ * [2] max lvl_bwd + 1. Asynchronous; max_passes + 2 small launches, passes after the fixed point return at once.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t dagnn_levels_workspace_bytes(int64_t N, int32_t max_passes);
+int dagnn_levels_build(const int64_t* edge_index, int64_t N, int64_t E, int32_t max_passes, int64_t* lvl_fwd, int64_t* lvl_bwd,
+                       int32_t* summary, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Parameter packing for one (direction, layer): GRU weights -> fp16 hi/lo split, pre-swizzled shared-memory images

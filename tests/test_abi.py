@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound(built_lib):
         assert hasattr(raw, name), "libdagnn_sm100.so does not export %s" % name
         assert name in _lib.EXPORTS, "%s is declared in the header but has no ctypes binding" % name
     assert sorted(_lib.EXPORTS) == declared
-    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 5
+    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_pack_layout_and_workspace_queries(built_lib):
@@ -46,6 +46,8 @@ def test_pack_layout_and_workspace_queries(built_lib):
     assert built_lib.dagnn_sweep_workspace_bytes(3, 2, 256, 256, 10, 10, 256) == 0   # dirs out of range
     assert built_lib.dagnn_schedule_workspace_bytes(1000, 2000, 256) > 0
     assert built_lib.dagnn_sweep_trace_bytes(10) == 11 * 256 * 16 * 8
+    assert built_lib.dagnn_levels_workspace_bytes(1000, 257) >= 4 * (2000 + 257)
+    assert built_lib.dagnn_levels_workspace_bytes(1000, 0) == 0                   # bad argument
 
 
 def test_no_cpu_path():

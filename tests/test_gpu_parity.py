@@ -305,3 +305,35 @@ def test_long_in_edge_lists_and_wide_states(n_src, n_dst, hid, dev):
             err = (st[d][i].cpu() - H_ref[d][i]).abs().max().item()
             assert err <= ATOL, "H[%d][%d] max-abs err %g" % (d, i, err)
     np.testing.assert_allclose(out.cpu().numpy(), out_ref.numpy(), atol=ATOL, rtol=0)
+
+
+def test_dag_levels_on_device_bit_exact(dev):
+    """Input side: longest-path levels computed on the device == the reference's `top_sort` /
+    `add_order_info_01` (golden level arrays of 12 graphs generated from src/utils_dag.py, tests/golden/levels.npz) and ==
+    the host restatement on whole batches: code2-shaped ASTs (levels on the AST edges only), a 3000-node chain (deeper
+    than the default number of passes: retried), no edges at all; a cycle raises like the host version."""
+    from dagnn_b200 import data as D, runtime as rt, _lib
+    import os
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "levels.npz"))
+    for k in range(12):
+        ei, n = z["ei_%d" % k], int(z["n_%d" % k])
+        l0, l1 = rt.dag_levels(torch.from_numpy(ei).to(dev), n)
+        assert l0.dtype == torch.int64 and np.array_equal(l0.cpu().numpy(), z["l0_%d" % k])
+        assert np.array_equal(l1.cpu().numpy(), z["l1_%d" % k])
+    B = D.make_code2_batch(24, 11)
+    ast = B.edge_index[:, B.edge_attr[:, 0] == 0]                    # ogb/io/read_graph_pyg.py:51: before augment_edge2
+    n = int(B.x.shape[0])
+    l0, l1 = rt.dag_levels(ast.to(dev), n)
+    assert torch.equal(l0.cpu(), B._bi_layer_idx0) and torch.equal(l1.cpu(), B._bi_layer_idx1)
+    assert np.array_equal(l0.cpu().numpy(), D.dag_levels_host(ast[0].numpy(), ast[1].numpy(), n))
+    assert np.array_equal(l1.cpu().numpy(), D.dag_levels_host(ast[1].numpy(), ast[0].numpy(), n))
+    chain = torch.stack([torch.arange(2999), torch.arange(1, 3000)])
+    l0, l1 = rt.dag_levels(chain.to(dev), 3000)
+    assert np.array_equal(l0.cpu().numpy(), np.arange(3000)) and np.array_equal(l1.cpu().numpy(), np.arange(3000)[::-1])
+    l0, l1 = rt.dag_levels(torch.zeros(2, 0, dtype=torch.long, device=dev), 5)
+    assert int(l0.abs().sum()) == 0 and int(l1.abs().sum()) == 0
+    with pytest.raises(ValueError):
+        rt.dag_levels(torch.tensor([[0, 1, 2], [1, 2, 0]], device=dev), 3)
+    with pytest.raises(_lib.DagnnError):
+        rt.dag_levels(torch.tensor([[0, 7], [1, 2]], device=dev), 3)
