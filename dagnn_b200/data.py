@@ -6,6 +6,7 @@ Nothing here is on the GPU hot path: these are the *inputs* either side of it (S
                           reference `forward(G)` reads (ogbg-code/model/dagnn.py:128-139, dvae/dagnn.py:99-114).
 * `dag_levels_host`     – longest-path level of every node (what `top_sort` computes,
                           src/utils_dag.py:8-35) for a whole disconnected batch at once, numpy.
+* `augment_edge2_batch` – `augment_edge2` (ogbg-code/utils2.py:31-79) on a collated batch, device-agnostic torch ops.
 * `make_code2_batch`    – seeded synthetic "ogbg-code2-shaped" AST batches:
                           ogbg-code2 itself is not available offline, so these are shape proxies.
 * `decode_enas_row` / `decode_bn_row` – the NA / BN text-row decoders (dvae/util.py:343-385 / :290-339).
@@ -69,6 +70,32 @@ def dag_levels_host(src: np.ndarray, dst: np.ndarray, n: int) -> np.ndarray:
             return lvl
         lvl = new
     raise ValueError("edge list is not acyclic")
+
+
+# --------------------------------------------------------------------------------------
+# augment_edge2 on a whole batch
+# --------------------------------------------------------------------------------------
+def augment_edge2_batch(edge_index_ast: torch.Tensor, node_is_attributed: torch.Tensor, batch: torch.Tensor):
+    """`augment_edge2` (ogbg-code/utils2.py:31-79) applied to every graph of an already collated batch, on whatever device
+    the tensors live on (index plumbing with torch ops, no host loop): next-token edges chain the consecutive attributed
+    nodes of each graph (nodes are in DFS order), `edge_attr` = [is next-token, is inverse] = [0, 0] for AST edges and
+    [1, 0] for next-token edges. The edges come back in the order per-graph augmentation followed by PyG collation gives:
+    graph by graph, AST edges first, then the graph's next-token edges (the order only fixes the summation order inside a
+    softmax). Returns (edge_index int64 [2, E'], edge_attr fp32 [E', 2])."""
+    dev = edge_index_ast.device
+    idx = torch.where(node_is_attributed.view(-1) == 1)[0]
+    if idx.numel() >= 2:
+        same = batch[idx[:-1]] == batch[idx[1:]]
+        nt = torch.stack([idx[:-1][same], idx[1:][same]], 0)
+    else:
+        nt = torch.zeros(2, 0, dtype=torch.long, device=dev)
+    ei = torch.cat([edge_index_ast, nt], 1)
+    kind = torch.cat([torch.zeros(edge_index_ast.shape[1], dtype=torch.long, device=dev),
+                      torch.ones(nt.shape[1], dtype=torch.long, device=dev)])
+    order = torch.argsort(batch[ei[0]] * 2 + kind, stable=True)
+    ei, kind = ei[:, order], kind[order]
+    ea = torch.stack([kind.float(), torch.zeros_like(kind, dtype=torch.float32)], 1)
+    return ei, ea
 
 
 # --------------------------------------------------------------------------------------

@@ -110,3 +110,24 @@ def test_gloo_world_size_2_sharding_and_gradient_allreduce():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+def test_augment_edge2_batch_equals_per_graph_augmentation_then_collation():
+    """ogbg-code/utils2.py:31-79 restated per graph (AST edges, then next-token edges between consecutive attributed
+    nodes; attrs [0,0] / [1,0]) + PyG collation (node offsets, graphs concatenated in order) == the batch-level helper."""
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 2, 12, 5]
+    eis, eas, asts, attrs, batch = [], [], [], [], []
+    off = 0
+    for gi, n in enumerate(sizes):
+        ast = torch.stack([torch.randint(0, n, (max(n - 1, 0),), generator=g), torch.arange(1, n)]) if n > 1 else torch.zeros(2, 0, dtype=torch.long)
+        is_attr = (torch.rand(n, generator=g) < 0.5).long()
+        idx = torch.where(is_attr == 1)[0]
+        nt = torch.stack([idx[:-1], idx[1:]]) if idx.numel() >= 2 else torch.zeros(2, 0, dtype=torch.long)
+        eis.append(torch.cat([ast, nt], 1) + off)
+        eas.append(torch.cat([torch.zeros(ast.shape[1], 2), torch.cat([torch.ones(nt.shape[1], 1), torch.zeros(nt.shape[1], 1)], 1)], 0))
+        asts.append(ast + off); attrs.append(is_attr); batch.append(torch.full((n,), gi, dtype=torch.long))
+        off += n
+    ei, ea = D.augment_edge2_batch(torch.cat(asts, 1), torch.cat(attrs).view(-1, 1), torch.cat(batch))
+    assert torch.equal(ei, torch.cat(eis, 1)) and torch.equal(ea, torch.cat(eas, 0))
+    assert ei.dtype == torch.int64 and ea.dtype == torch.float32
