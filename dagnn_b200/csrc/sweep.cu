@@ -41,7 +41,7 @@ constexpr int kTmemCols = 512;                           // 2 sub-tiles x 256 co
 constexpr int kMaxChunks = 16;                           // k chunks of a tile that may use compact operand stages
 constexpr int kCoopEdges = 10;     // gate phase: nodes with more in-edges are aggregated by the whole CTA (split by columns)
 constexpr int kMaxCoop = 48;       // ... per CTA and gate phase; beyond that a warp does the node alone
-constexpr int kScanRows = 2048;    // steps with at most this many rows are latency-bound: their long in-edge lists are found a
+constexpr int kScanRows = 4096;    // steps with at most this many rows are latency-bound: their long in-edge lists are found a
 constexpr int kMaxHeavy = 128;     // phase ahead (at most this many) and get a CTA of their own, from the start of the phase
 constexpr int kMaxSmem = 232448;                         // 227 KB opt-in limit per CTA on sm_100
 
