@@ -1,4 +1,7 @@
 """Profiling helper: which CTAs are the slowest in the gate phase of a step, and what rows (in-degrees) they were dealt.
+The row listing reproduces the plain dealing rule (every CTA takes rows); in steps where long in-edge lists get CTAs of
+their own (<= 4096 rows, see scan_heavy in csrc/sweep.cu) the first CTAs hold those nodes instead — the times are right
+either way.
     python tools/trace_gate_balance.py [workload] [step ...]      (GPU box)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
