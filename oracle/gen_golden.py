@@ -40,6 +40,13 @@ OGB_CASES = [
          pool_all=0, pool="max", wea=True, num_class=0, wseed=1),
     dict(name="ogb_code2_h300x5", gen=("code2", 3, 20263), emb=300, hid=300, layers=5, bidir=True, out_wx=False,
          pool_all=0, pool="max", wea=True, num_class=0, wseed=2, states=False),
+    # hidden width that is not a multiple of 4, a single layer, add pooling
+    dict(name="ogb_rand_h30_l1_add", gen=("rand", 5, 19), emb=12, hid=30, layers=1, bidir=True, out_wx=False,
+         pool_all=0, pool="add", wea=True, num_class=0, wseed=13),
+    # 3 H that is not a multiple of 64, three layers, mean over all nodes (out_wx with out_pool_all does not run in the
+    # reference: its head is sized for one direction's width more than the readout produces)
+    dict(name="ogb_code2_h72_l3_mean_all", gen=("code2", 4, 20265), emb=48, hid=72, layers=3, bidir=True, out_wx=False,
+         pool_all=1, pool="mean", wea=True, num_class=0, wseed=14),
 ]
 
 DVAE_CASES = [
@@ -51,6 +58,7 @@ DVAE_CASES = [
     dict(name="bn_real_hs501", kind="BN", rows=("asia_200k.txt", 0, 128), hs=501, layers=2, bidir=True, wseed=11,
          states=False),
     dict(name="bn_real_unidir_hs40", kind="BN", rows=("asia_200k.txt", 300, 24), hs=40, layers=2, bidir=False, wseed=12),
+    dict(name="na_real_unidir_l3_hs36", kind="NA", rows=("final_structures6.txt", 2000, 24), hs=36, layers=3, bidir=False, wseed=15),
 ]
 
 
@@ -201,11 +209,15 @@ def main():
     if not ref_loader.available():
         raise SystemExit("reference checkout not found (set $DAGNN_REFERENCE)")
     os.makedirs(OUT, exist_ok=True)
-    gen_levels()
+    only = set(sys.argv[1:])            # optional: names of the fixtures to (re)generate
+    if not only:
+        gen_levels()
     for c in OGB_CASES:
-        gen_ogb(c)
+        if not only or c["name"] in only:
+            gen_ogb(c)
     for c in DVAE_CASES:
-        gen_dvae(c)
+        if not only or c["name"] in only:
+            gen_dvae(c)
 
 
 if __name__ == "__main__":

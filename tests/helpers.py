@@ -53,6 +53,6 @@ def dvae_module_from_meta(meta, device=None):
 
 
 OGB_GOLDEN = ["ogb_rand_bidir", "ogb_rand_unidir3", "ogb_rand_noattr_mean", "ogb_rand_wx_add_cls", "ogb_code2_small",
-              "ogb_code2_h300x5"]
+              "ogb_code2_h300x5", "ogb_rand_h30_l1_add", "ogb_code2_h72_l3_mean_all"]
 DVAE_GOLDEN = ["na_real_hs64", "na_real_hs501", "na_real_bidir_hs48", "bn_real_hs64", "bn_real_hs501",
-               "bn_real_unidir_hs40"]
+               "bn_real_unidir_hs40", "na_real_unidir_l3_hs36"]
