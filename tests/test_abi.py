@@ -48,6 +48,10 @@ def test_pack_layout_and_workspace_queries(built_lib):
     assert built_lib.dagnn_sweep_trace_bytes(10) == 11 * 256 * 16 * 8
     assert built_lib.dagnn_levels_workspace_bytes(1000, 257) >= 4 * (2000 + 257)
     assert built_lib.dagnn_levels_workspace_bytes(1000, 0) == 0                   # bad argument
+    # argument validation comes before any CUDA call: error code + message, nothing launched
+    n0 = built_lib.dagnn_launch_count()
+    assert built_lib.dagnn_levels_build(None, 10, 0, 4, None, None, None, None, 0, None) != 0
+    assert b"levels" in built_lib.dagnn_last_error() and built_lib.dagnn_launch_count() == n0
 
 
 def test_no_cpu_path():
