@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdagnn_sm100.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "tc_selftest.cu"]
-HEADERS = ["common.cuh", "tc.cuh"]
+SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "sweep_cluster.cu", "tc_selftest.cu"]
+HEADERS = ["common.cuh", "sync.cuh", "tc.cuh"]
 
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 vp = C.c_void_p
 
@@ -69,7 +69,7 @@ EXPORTS = {
     "dagnn_last_error": (C.c_char_p, []),
     "dagnn_launch_count": (C.c_int64, []),
     "dagnn_operand_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
-    "dagnn_embed_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
+    "dagnn_embed_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
     "dagnn_levels_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "dagnn_levels_build": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_size_t, vp]),
     "dagnn_schedule_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
@@ -79,8 +79,8 @@ EXPORTS = {
     "dagnn_sweep_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
     "dagnn_sweep_trace_bytes": (C.c_size_t, [C.c_int32]),
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
-    "dagnn_tc_selftest_f32": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dagnn_tc_selftest_f16x3": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dagnn_tc_selftest_ts": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),
     "dagnn_states_to_node_order_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.c_int32, vp, C.c_int64, C.c_int32, vp,

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "dagnn_b200.h"
 
@@ -32,6 +33,27 @@ inline int check_launch(const char* what) {
   do {                                                                        \
     if (!(cond)) return dagnn::set_err(DAGNN_E_INVALID, "%s (%s)", msg, #cond); \
   } while (0)
+
+// Function attributes (dynamic shared memory limit, cluster opt-in) are per device: run `f` once per device ordinal,
+// thread-safe (the reference's DataParallel calls forward from one host thread per GPU, tg/data_parallel.py:60-61).
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+};
+template <typename F>
+inline int per_device_once(PerDeviceOnce& o, int* dev_out, F&& f) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_err(DAGNN_E_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= kMaxDevices) return set_err(DAGNN_E_UNSUPPORTED, "device ordinal %d", dev);
+  if (dev_out) *dev_out = dev;
+  std::lock_guard<std::mutex> lk(o.mu);
+  if (o.done[dev]) return DAGNN_OK;
+  const int rc = f(dev);
+  if (rc == DAGNN_OK) o.done[dev] = true;
+  return rc;
+}
 
 __host__ __device__ inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

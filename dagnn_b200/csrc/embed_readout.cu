@@ -10,18 +10,34 @@ namespace dagnn {
 template <bool VEC4>
 __global__ void __launch_bounds__(256) k_embed(const int64_t* __restrict__ x, const int64_t* __restrict__ depth,
                                                const float* __restrict__ T, const float* __restrict__ A,
-                                               const float* __restrict__ P, int max_depth, int N, int D,
-                                               float* __restrict__ X, int64_t ldx, unsigned char* __restrict__ ximg) {
+                                               const float* __restrict__ P, int max_depth, long long n_types, long long n_attrs,
+                                               int N, int D, float* __restrict__ X, int64_t ldx,
+                                               unsigned char* __restrict__ ximg) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int v = blockIdx.x * wpb + (threadIdx.x >> 5); v < N; v += gridDim.x * wpb) {
     const long long t = x[2 * (size_t)v], a = x[2 * (size_t)v + 1];
     long long dp = depth[v];
     dp = dp > max_depth ? max_depth : dp;
+    float* o = X + (size_t)v * ldx;
+    // an index outside its table (nn.Embedding raises IndexError there, ogbg-code/utils.py:27): nothing is read out of
+    // bounds, the row becomes NaN and every output that depends on it is NaN — loud, not silently wrong
+    if (t < 0 || t >= n_types || a < 0 || a >= n_attrs || dp < 0) {
+      for (int c = lane; c < D; c += 32) o[c] = __int_as_float(0x7fc00000);
+      if (VEC4 && ximg) {
+        const int nck = (D + 63) >> 6;
+        unsigned char* itile = ximg + (size_t)(v >> 7) * nck * (2 * 128 * tc::ROW_BYTES);
+        for (int c = lane * 4; c < nck * 64; c += 128) {
+          unsigned char* ihi = itile + (size_t)(c >> 6) * (2 * 128 * tc::ROW_BYTES) + tc::tile_off(v & 127, (c & 63) >> 3) + (c & 4) * 2;
+          *reinterpret_cast<uint2*>(ihi) = make_uint2(0x7e007e00u, 0x7e007e00u);       // fp16 NaN
+          *reinterpret_cast<uint2*>(ihi + 128 * tc::ROW_BYTES) = make_uint2(0u, 0u);
+        }
+      }
+      continue;
+    }
     const float* tr = T + (size_t)t * D;
     const float* ar = A + (size_t)a * D;
     const float* pr = P + (size_t)dp * D;
-    float* o = X + (size_t)v * ldx;
     if (VEC4) {
       // optional second copy of the row: fp16 hi / lo halves in the tcgen05 operand-image layout the sweep's first
       // projection bulk-copies (128-node tiles x 64-wide k chunks, 32 KB each; k padding zero-filled)
@@ -61,6 +77,7 @@ struct ReadoutArgs {
   DagnnReadoutBlock blk[DAGNN_MAX_READOUT_BLOCKS];
   const int* pos[DAGNN_MAX_DIRS];
   const int* gptr;
+  const int* summary;        // [2] != 0: the schedule is unusable (level table overflow / bad indices), nothing is read
 };
 
 // grid (B, nblocks, column chunks of 128), 256 threads: warp w scans nodes [v0 + 32w, v0 + 32w + 32) (+256 ...) of the
@@ -72,7 +89,7 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ Readout
   const int g = blockIdx.x;
   const DagnnReadoutBlock& b = a.blk[blockIdx.y];
   const int c0 = blockIdx.z * 128;
-  if (c0 >= b.width) return;
+  if (c0 >= b.width || a.summary[2] != 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v0 = a.gptr[g], v1 = a.gptr[g + 1];
   const int* pos = b.index_mode ? a.pos[b.dir] : nullptr;
@@ -135,18 +152,19 @@ extern "C" size_t dagnn_operand_image_bytes(int64_t N, int32_t D) {
 }
 
 extern "C" int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
-                               const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* x_image,
-                               void* stream_) {
+                               const float* depth_tab, int max_depth, int64_t n_types, int64_t n_attrs, int64_t N, int D, float* X,
+                               int64_t ldx, void* x_image, void* stream_) {
   DAGNN_REQUIRE(x && depth && type_tab && attr_tab && depth_tab && X, "embed: null pointer");
-  DAGNN_REQUIRE(N > 0 && N < (1ll << 31) && D > 0 && ldx >= D && max_depth >= 0, "embed: sizes");
+  DAGNN_REQUIRE(N > 0 && N < (1ll << 31) && D > 0 && ldx >= D && max_depth >= 0 && n_types > 0 && n_attrs > 0, "embed: sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && ((((uintptr_t)type_tab | (uintptr_t)attr_tab | (uintptr_t)depth_tab | (uintptr_t)X) & 15) == 0);
   if (x_image && (!vec || ((uintptr_t)x_image & 1023) != 0))
     return set_err(DAGNN_E_INVALID, "embed: the operand image needs D %% 4 == 0, 16-byte aligned tables / X and a 1024-byte aligned image");
   const int blocks = (int)((N + 7) / 8 < 148 * 16 ? (N + 7) / 8 : 148 * 16);
-  if (vec) k_embed<true><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx,
+  if (vec) k_embed<true><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, n_types, n_attrs, (int)N, D, X, ldx,
                                                   static_cast<unsigned char*>(x_image));
-  else k_embed<false><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, (int)N, D, X, ldx, nullptr);
+  else k_embed<false><<<blocks, 256, 0, st>>>(x, depth, type_tab, attr_tab, depth_tab, max_depth, n_types, n_attrs, (int)N, D, X, ldx,
+                                         nullptr);
   return check_launch("k_embed");
 }
 
@@ -155,10 +173,11 @@ extern "C" int dagnn_readout_f32(const DagnnSchedule* s, const DagnnReadoutBlock
   DAGNN_REQUIRE(s && blocks && out, "readout: null pointer");
   DAGNN_REQUIRE(nblocks > 0 && nblocks <= DAGNN_MAX_READOUT_BLOCKS, "readout: nblocks");
   DAGNN_REQUIRE(pool >= 0 && pool <= 2, "readout: pool");
-  DAGNN_REQUIRE(s->B > 0 && s->gptr, "readout: schedule has no graph pointers");
+  DAGNN_REQUIRE(s->B > 0 && s->gptr && s->summary, "readout: schedule has no graph pointers");
   ReadoutArgs a;
   a.nblocks = nblocks; a.pool = pool; a.B = (int)s->B;
   a.gptr = s->gptr;
+  a.summary = s->summary;
   for (int d = 0; d < DAGNN_MAX_DIRS; ++d) a.pos[d] = d < s->dirs ? s->pos[d] : nullptr;
   int maxw = 0;
   for (int i = 0; i < nblocks; ++i) {

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(32) k_sched_place(const int64_t* __restrict__ 
       }
       base = __shfl_sync(peers, base, __ffs(peers) - 1);
       const long long node = nid ? nid[k] : (long long)k;
+      if (node != k) summary[3] = 1;        // positions inside a level are not in node-id order (the cluster sweep cuts groups by it)
       if (node < 0 || node >= N) {
         summary[2] = 2;
       } else {
@@ -121,6 +122,9 @@ __global__ void __launch_bounds__(32) k_sched_place(const int64_t* __restrict__ 
 __global__ void k_sched_degree(const int64_t* __restrict__ ei, int E, int N, int dirs, const int* __restrict__ pos0,
                                const int* __restrict__ pos1, int* __restrict__ deg0, int* __restrict__ deg1,
                                int* __restrict__ summary) {
+  // a level outside the table (status 1) or a bad node id (2) leaves pos[] entries unset: no CSR is built then (the sweep and
+  // the readout skip such a schedule too; the host raises or rebuilds with a larger level table)
+  if (*reinterpret_cast<volatile int*>(summary + 2) == 1) return;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < E * dirs; idx += gridDim.x * blockDim.x) {
     const int d = idx / E, e = idx - d * E;
     const long long t = ei[(size_t)(1 - d) * E + e], o = ei[(size_t)d * E + e];
@@ -140,7 +144,9 @@ __global__ void __launch_bounds__(kScanThreads) k_sched_rowptr(int* deg0, int* d
 
 __global__ void k_sched_fill(const int64_t* __restrict__ ei, int E, int N, int dirs, const int* __restrict__ pos0,
                              const int* __restrict__ pos1, const int* __restrict__ rowptr0, const int* __restrict__ rowptr1,
-                             int* __restrict__ cur0, int* __restrict__ cur1, int* __restrict__ tmp0, int* __restrict__ tmp1) {
+                             int* __restrict__ cur0, int* __restrict__ cur1, int* __restrict__ tmp0, int* __restrict__ tmp1,
+                             const int* __restrict__ summary) {
+  if (summary[2] != 0) return;          // set by earlier launches only (k_sched_degree is complete)
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < E * dirs; idx += gridDim.x * blockDim.x) {
     const int d = idx / E, e = idx - d * E;
     const long long t = ei[(size_t)(1 - d) * E + e], o = ei[(size_t)d * E + e];
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(256) k_sched_rows(const int64_t* __restrict__ 
                                                     const int* __restrict__ rowptr0, const int* __restrict__ rowptr1,
                                                     const int* __restrict__ tmp0, const int* __restrict__ tmp1, int* __restrict__ eid0,
                                                     int* __restrict__ eid1, int* __restrict__ col0, int* __restrict__ col1,
-                                                    float* __restrict__ ea0, float* __restrict__ ea1) {
+                                                    float* __restrict__ ea0, float* __restrict__ ea1, const int* __restrict__ summary) {
+  if (summary[2] != 0) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < N * dirs; w += gridDim.x * warps_per_block) {
@@ -267,6 +274,7 @@ extern "C" int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lv
 
   DAGNN_CUDA_OK(cudaMemsetAsync(workspace, 0, (size_t)((char*)w.tmp[0] - (char*)workspace), st));  // cnt + deg
   DAGNN_CUDA_OK(cudaMemsetAsync(s->summary, 0, 8 * sizeof(int), st));
+  for (int d = 0; d < s->dirs; ++d) DAGNN_CUDA_OK(cudaMemsetAsync(s->pos[d], 0, (size_t)s->N * sizeof(int), st));   // never garbage
   int* lo1 = dirs == 2 ? s->lvl_off[1] : s->lvl_off[0];
   int *perm1 = dirs == 2 ? s->perm[1] : s->perm[0], *pos1 = dirs == 2 ? s->pos[1] : s->pos[0];
   int* rp1 = dirs == 2 ? s->rowptr[1] : s->rowptr[0];
@@ -288,12 +296,13 @@ extern "C" int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lv
   if (E > 0) {
     const int eb = min(1184, ceil_div(E * dirs, 256));
     k_sched_fill<<<eb, 256, 0, st>>>(edge_index, E, N, dirs, s->pos[0], pos1, s->rowptr[0], rp1, w.deg[0], w.deg[1], w.tmp[0],
-                                     w.tmp[1]);
+                                     w.tmp[1], s->summary);
     if (int rc = check_launch("k_sched_fill")) return rc;
     const int rb = min(148 * 8, ceil_div(N * dirs, 8));
     k_sched_rows<<<rb, 256, 0, st>>>(edge_index, edge_attr, E, N, dirs, s->pos[0], pos1, s->rowptr[0], rp1, w.tmp[0], w.tmp[1],
                                      s->eid[0], dirs == 2 ? s->eid[1] : s->eid[0], s->col[0], dirs == 2 ? s->col[1] : s->col[0],
-                                     edge_attr ? s->eattr[0] : nullptr, edge_attr ? (dirs == 2 ? s->eattr[1] : s->eattr[0]) : nullptr);
+                                     edge_attr ? s->eattr[0] : nullptr, edge_attr ? (dirs == 2 ? s->eattr[1] : s->eattr[0]) : nullptr,
+                                     s->summary);
     if (int rc = check_launch("k_sched_rows")) return rc;
   }
   if (s->B > 0) {

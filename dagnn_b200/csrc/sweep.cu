@@ -21,10 +21,19 @@
 //                N = 64..256, fp16 x 3 split, fp32 accumulators in TMEM); the builder warps drain TMEM into P / Gi rows.
 // States written in one phase are read in later phases by OTHER CTAs: all such reads use ld.global.cg (L2), the
 // barrier is the cooperative-groups pattern (bar.sync; fence; atomic; spin on ld.acquire; bar.sync).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
+#include "sync.cuh"
 #include "tc.cuh"
 
 namespace dagnn {
+
+// sweep_cluster.cu: the cluster-resident sweep (H, Din <= 256); `handled` = false leaves the launch to the grid-wide kernel below
+bool cluster_path_supported(int dirs, int layers, int Din, int H, int nvid);
+size_t cluster_workspace_bytes(int dirs, int layers, int Din, int H, int64_t N, int32_t max_levels);
+int cluster_forward(const DagnnSweepArgs* A, cudaStream_t st, bool* handled);
 
 constexpr int kBuilderWarps = 8;
 constexpr int kBuilders = kBuilderWarps * 32;            // 256 threads: gate phase, operand build, epilogue
@@ -117,39 +126,6 @@ struct SmemTail {
 constexpr size_t kSmemBytes = 1024 + (size_t)kNAS * kAStageBytes + kBRegionBytes + sizeof(SmemTail);
 static_assert(kSmemBytes <= (size_t)kMaxSmem, "shared memory plan exceeds the 227 KB opt-in limit");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or the hint expires)
-// instead of spinning next to the single MMA-issuing thread
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity), "r"(0x989680u)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // all CTAs of the (cooperative, co-resident) grid; `target` = arrivals expected so far
 // Only the builder warps write global memory, so they alone gate the arrival (named barrier 1); the issuer warp, which may
 // still be queueing weight prefetches, joins at the closing CTA-wide barrier.
@@ -165,18 +141,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   }
   __syncthreads();
 }
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
-  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // gate phase: one warp per node. Lane l owns the units 4 l + 128 j (+ 0..3), j < J, of a 128 J wide column pass.
 // The chain of dependent L2 round trips is what a node costs (~0.3-0.5 us each), so everything that does not depend
@@ -735,14 +699,6 @@ __device__ __forceinline__ void ring_load(const Tile& T, int nbc, int c, unsigne
 // (`leader`) alone starts copies, MMAs and commits. The operands of tcgen05.mma live in uniform registers; values the
 // compiler cannot prove warp-uniform (anything derived from the shared-memory step table) pass through uni() first,
 // otherwise every MMA is wrapped in a ~100-cycle elect / broadcast loop and a 64-column tile is issue-bound.
-__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
-// one lane of the converged warp (always the same one). Guarding the single-thread instructions with elect.sync rather
-// than lane == 0 lets ptxas drop its own elect loop around every tcgen05.mma (65 -> 42 cycles per issue, tools/ubench_mma.cu)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void issuer_tile(const Tile& T, int nbc, unsigned char* As, unsigned char* Bs, SmemTail& S, uint32_t tmem,
                                             uint32_t ja, uint32_t cs, uint32_t ct, RingState& R, bool leader, bool prev_small,
                                             long long* tr) {
@@ -1186,8 +1142,10 @@ extern "C" size_t dagnn_sweep_workspace_bytes(int32_t dirs, int32_t layers, int3
     return 0;
   const size_t Mc = (size_t)round_up(3 * round_up(H, 4), 64);
   // per (direction, layer): key scores [N], hidden projection P [N, Mc], input projection Gi [N, Mc], operand image of H
-  return 256 + (size_t)dirs * layers * (align256((size_t)N * sizeof(float)) + 2 * align256((size_t)N * Mc * sizeof(float)) +
-                                        aimg_bytes(H, N, max_levels));
+  const size_t grid_wide = 256 + (size_t)dirs * layers * (align256((size_t)N * sizeof(float)) + 2 * align256((size_t)N * Mc * sizeof(float)) +
+                                                          aimg_bytes(H, N, max_levels));
+  const size_t cluster = cluster_workspace_bytes(dirs, layers, Din, H, N, max_levels);   // either kernel may take the launch
+  return grid_wide > cluster ? grid_wide : cluster;
 }
 extern "C" size_t dagnn_sweep_trace_bytes(int32_t max_steps) { return (size_t)(max_steps + 1) * 256 * 16 * sizeof(long long); }
 
@@ -1206,6 +1164,22 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
   if (H < 1 || H > 4096) return set_err(DAGNN_E_UNSUPPORTED, "sweep: hidden size %d not in [1,4096]", H);
   if (A->nvid < 0) return set_err(DAGNN_E_INVALID, "sweep: nvid");
   if (S->N >= (1ll << 31)) return set_err(DAGNN_E_UNSUPPORTED, "sweep: more than 2^31 nodes");
+  for (int d = 0; d < dirs; ++d) {
+    DAGNN_REQUIRE(S->perm[d] && S->rowptr[d] && S->lvl_off[d] && (S->E == 0 || S->col[d]), "sweep: schedule arrays");
+    DAGNN_REQUIRE(!A->use_edge_attr || S->E == 0 || S->eattr[d], "sweep: schedule carries no edge attributes");
+    for (int i = 0; i < layers; ++i) {
+      DAGNN_REQUIRE(A->Hs[d][i] && ((uintptr_t)A->Hs[d][i] & 15) == 0, "sweep: state buffers must be 16-byte aligned");
+      DAGNN_REQUIRE(A->packed[d][i] && ((uintptr_t)A->packed[d][i] & 15) == 0, "sweep: packed params must be 16-byte aligned");
+    }
+  }
+  // DAGNN_SWEEP_PATH=grid forces the grid-wide kernel (A/B measurements, tests of both kernels); default: the cluster-resident
+  // sweep whenever the shape fits it
+  const char* path_env = getenv("DAGNN_SWEEP_PATH");
+  if (!(path_env && strcmp(path_env, "grid") == 0)) {
+    bool handled = false;
+    if (int rc = cluster_forward(A, st, &handled)) return rc;
+    if (handled) return DAGNN_OK;
+  }
   SweepP P;
   memset(&P, 0, sizeof(P));
   DagnnPackLayout lay[DAGNN_MAX_LAYERS];
@@ -1243,19 +1217,20 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
     }
   }
 
+  static PerDeviceOnce once;
+  static int sm_count[kMaxDevices] = {0};
   int dev = 0;
-  DAGNN_CUDA_OK(cudaGetDevice(&dev));
-  static int sm_count[64] = {0};
-  if (dev >= 64) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device ordinal %d", dev);
-  if (sm_count[dev] == 0) {
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    int n = 0, coop = 0;
-    DAGNN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    DAGNN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (!coop) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device has no cooperative launch");
-    sm_count[dev] = n;
-  }
+  if (int rc = per_device_once(once, &dev, [&](int dv) {
+        DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        DAGNN_CUDA_OK(cudaFuncSetAttribute(k_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        int n = 0, coop = 0;
+        DAGNN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dv));
+        DAGNN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dv));
+        if (!coop) return set_err(DAGNN_E_UNSUPPORTED, "sweep: device has no cooperative launch");
+        sm_count[dv] = n;
+        return (int)DAGNN_OK;
+      }))
+    return rc;
   const int G = sm_count[dev];
   DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 16, st));
   void* kargs[] = {(void*)&P};

@@ -1,0 +1,723 @@
+// The DAGNN level sweep, cluster-resident: one thread-block cluster of 8 CTAs per (layer, direction, graph group) walks its
+// levels with the GRU weights pinned on chip, "aggregate, then project".
+//
+// Why: the grid-wide sweep (sweep.cu) pays two grid barriers, a weight stream and a tile set-up per wavefront step — ~20 us
+// per step on a chain of L + layers - 1 steps, whatever the step holds (profiles/r1h_summary.md). Graphs are independent and
+// a level of one graph group is small, so the whole recurrence of a (layer, direction, group) fits one cluster:
+//   * the CTA of cluster rank c owns U = H/8 hidden units (all three gates): its slice of W_hh lives in TENSOR MEMORY as the
+//     A operand of tcgen05.mma (fp16 hi tile + lo tile, 96 lanes x K/2 columns each), its slice of W_ih in SHARED MEMORY
+//     (K-major SWIZZLE_128B hi / lo tiles) — loaded once, never streamed again;
+//   * per level:  gather phase — the rows of the level are dealt to the 64 worker warps of the cluster; a warp gathers the
+//                 full predecessor rows h_j of its node (CSR, one 16-byte pair per lane), scores them on the fly
+//                 (wk . h_j + edge terms), softmax, m_v = sum_e alpha_e h_j, and stores m_v as an fp16 hi/lo operand row (+ fp32);
+//                 layer 0 also converts the node's input row x_v into an operand row;
+//                 cluster barrier;
+//                 projection — every CTA bulk-copies the operand rows of the level (cp.async.bulk, 128 rows x 64 k per
+//                 stage) and issues D[gate unit, node] = W_ih x_v (SS) and W_hh m_v (TS, weights from TMEM), three split
+//                 products each, fp32 accumulators in TMEM;
+//                 epilogue — TMEM -> shared-memory transpose -> GRU pointwise for the CTA's units, h_v stored as fp32
+//                 (position order, the output) and, for the next layer, as an operand row;
+//                 cluster barrier.
+//   * stacked layers pipeline across clusters: cluster (i, d, g) waits for cluster (i - 1, d, g) to publish level l through a
+//     release/acquire counter in global memory; work items are ordered layer-major so that a cluster only ever waits for
+//     lower-numbered clusters (no co-residency assumption needed for progress).
+// HBM traffic is the algorithmic one (input row, predecessor rows, state row) plus the operand rows (fp16 hi/lo copies).
+// Nothing of P = W_hh h / Gi = W_ih x is materialised.
+//
+// Replaces ogbg-code/model/dagnn.py:144-182 incl. AttnConv (:362-373), PyG propagate / softmax / scatter-add, nn.GRUCell (:181)
+// and the index_put at :182; D-VAE variants dvae/dagnn.py:109-145, dvae/dagnn_bn.py:108-136 — same contract as sweep.cu.
+#include "common.cuh"
+#include "sync.cuh"
+#include "tc.cuh"
+
+namespace dagnn {
+
+constexpr int kCWorkWarps = 8;
+constexpr int kCWorkers = kCWorkWarps * 32;        // gather phase, epilogue
+constexpr int kCThreads = kCWorkers + 32;          // + the warp that issues bulk copies and MMAs
+constexpr int kCS = 8;                             // CTAs per cluster
+constexpr int kCMaxH = 256;                        // K of an operand row: 4 chunks of 64
+constexpr int kCU = kCMaxH / kCS;                  // hidden units per CTA at most (3 * 32 = 96 TMEM lanes)
+constexpr int kRC = 128;                           // rows per projection chunk (N of the MMAs)
+constexpr int kCStageBytes = 2 * kRC * tc::ROW_BYTES;      // hi + lo tile of 128 rows x 64 k = 32 KB
+constexpr int kCNStage = 3;
+constexpr int kWRows = 96;                         // W_ih slice rows: gate * 32 + unit
+constexpr int kWChunkBytes = kWRows * tc::ROW_BYTES;       // 12 KB per (plane, k chunk)
+constexpr int kWBytes = 2 * 4 * kWChunkBytes;              // 96 KB
+constexpr int kSub = 32;                           // rows per epilogue pass
+constexpr int kSLd = 33;                           // stage row pitch (words): conflict-free both ways
+constexpr int kColWhi = 0, kColWlo = 128, kColAccX = 256, kColAccH = 384;   // TMEM column map (512 allocated)
+constexpr int kCMaxItems = 15;                     // 8-CTA clusters of this footprint resident on a B200 (tools/probe_cluster.cu)
+
+struct CDir {
+  const int* perm;      // position -> node id
+  const int* rowptr;    // [N+1] CSR rows by position
+  const int* col;       // [E] neighbour position
+  const float* eattr;   // [E,2] in CSR order or nullptr
+  const int* lvl_off;   // [max_levels+1]
+};
+struct CLay {
+  float* Hs;                   // H[d][i], [N, ldh] position order
+  unsigned char* himg;         // operand rows of H[d][i] (written when a next layer exists)
+  unsigned char* mimg;         // operand rows of the aggregates m
+  float* m32;                  // [N, ldh] the aggregates in fp32 (z * m term of the cell)
+  const float* bias;           // [4][HP]
+  const float* wk;             // [HP]
+  const float* attnc;          // [4]
+  const float* vidk;           // [nvid]
+  const __half* w_hh;          // packed image holding W_hh^i (columns [0, Mc))
+  const __half* w_ih;          // packed image holding W_ih^i, first column ih_col0
+  int ih_col0, ih_nck;         // ... and its k chunks per column block
+};
+struct ClusterP {
+  int dirs, layers, G, H, Hq, Mc, HP, nvid, use_ea, Din, N, B;
+  int U;                       // hidden units per CTA (multiple of 4, <= 32)
+  int Kh, Kx;                  // operand widths padded to 16 (state / layer-0 input)
+  int nckh, nckx;              // 64-k chunks of those
+  int vec_x, max_levels;
+  long long ldh, ldx, Q;       // Q: rows of an operand-row plane
+  const float* X;              // [N, ldx] node order
+  unsigned char* ximg[DAGNN_MAX_DIRS];   // operand rows of X in the position order of each direction
+  const int* summary;          // [0] levels, [2] status, [3] node ids are not the identity
+  const int* gptr;             // [B+1]
+  int4* tab;                   // [items][max_levels + 1] per level: first position, rows, first operand row, level start
+  unsigned int* flags;         // [items] levels published
+  long long* trace;            // optional [levels][256][16] clock64 stamps per (level, CTA): 0 start, 1 gathered, 2 exchanged,
+                               // 3 projected + cells done, 4 level closed
+  CDir dir[DAGNN_MAX_DIRS];
+  CLay lay[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
+};
+
+struct CSmemTail {
+  float stage[2][kWRows][kSLd];     // epilogue transpose: [accumulator][gate * 32 + unit][row of the pass]
+  float bias[4][kCU];
+  uint64_t full[kCNStage], empty[kCNStage], acc_full, tmem_free;
+  uint32_t tmem_slot;
+};
+constexpr size_t kCSmemBytes = 1024 + (size_t)kWBytes + (size_t)kCNStage * kCStageBytes + sizeof(CSmemTail);
+static_assert(kCSmemBytes <= 232448, "shared memory plan exceeds the 227 KB opt-in limit");
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_idx() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCWorkers) : "memory"); }
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// address of the 16-byte granule holding k = [8 gk, 8 gk + 8) of operand row q (plane 0 = hi, 1 = lo): planes of k chunks of
+// rows, a row = 128 bytes = 64 k, granules XOR-swizzled with the row index like the shared-memory tile they are copied into
+__device__ __forceinline__ unsigned char* oprow_ptr(unsigned char* img, int plane, int nck, long long Q, long long q, int gk) {
+  return img + ((((size_t)plane * nck + (gk >> 3)) * (size_t)Q + (size_t)q) << 7) + (((gk & 7) ^ ((int)q & 7)) << 4);
+}
+// 8 fp16 weights W[col, 8 gk .. 8 gk + 8) from a packed projection image (pack.cu: 64-column blocks x 64-k chunks, hi then lo tile)
+__device__ __forceinline__ uint4 packed_w8(const __half* img, int nck, int col, int gk, int plane) {
+  const int cb = col >> 6, j = col & 63;
+  const size_t off = (((size_t)cb * nck + (gk >> 3)) * 2 + plane) * 4096 + (size_t)(j >> 3) * 512 + (size_t)(j & 7) * 64 +
+                     (size_t)(((gk & 7) ^ (j & 7)) << 3);
+  return __ldg(reinterpret_cast<const uint4*>(img + off));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gather phase: one warp per node. Lane l owns k = [8 l, 8 l + 8) of a row.
+// ------------------------------------------------------------------------------------------------------------
+struct Row8 { float v[8]; };
+
+__device__ __forceinline__ void load_row8(Row8& R, const float* __restrict__ row, int k0, int width4) {
+  // width4 = valid floats of the row rounded up to 4 (rows are zero padded to it)
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (k0 + 4 <= width4) a = ldcg4(row + k0);
+  if (k0 + 8 <= width4) b = ldcg4(row + k0 + 4);
+  R.v[0] = a.x; R.v[1] = a.y; R.v[2] = a.z; R.v[3] = a.w; R.v[4] = b.x; R.v[5] = b.y; R.v[6] = b.z; R.v[7] = b.w;
+}
+__device__ __forceinline__ float dot8(const Row8& R, const float (&w)[8]) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s = fmaf(R.v[j], w[j], s);
+  return s;
+}
+__device__ __forceinline__ void store_oprow(unsigned char* img, int nck, long long Q, long long q, int lane, const float (&v)[8]) {
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(oprow_ptr(img, 0, nck, Q, q, lane)) = hi;
+  *reinterpret_cast<uint4*>(oprow_ptr(img, 1, nck, Q, q, lane)) = lo;
+}
+
+// x_v -> operand row (layer 0)
+__device__ __forceinline__ void convert_x_row(const ClusterP& P, const CDir& D, int d, int p, long long q, int lane) {
+  if (8 * lane >= P.Kx) return;
+  const float* src = P.X + (size_t)D.perm[p] * P.ldx;
+  float v[8];
+  const int k0 = 8 * lane;
+  if (P.vec_x) {
+    Row8 R;
+    load_row8(R, src, k0, (P.Din + 3) & ~3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = R.v[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < P.Din) ? __ldcg(src + k0 + j) : 0.f;
+  }
+  store_oprow(P.ximg[d], P.nckx, P.Q, q, lane, v);
+}
+
+// score of one in-edge apart from the key term: edge type + vertex id (constants per destination cancel)
+__device__ __forceinline__ float edge_terms(const ClusterP& P, const CDir& D, const CLay& Lp, int e, int sp, float ca0, float ca1) {
+  float sc = 0.f;
+  if (D.eattr) {
+    const float2 ea = __ldg(reinterpret_cast<const float2*>(D.eattr) + e);
+    sc = ca0 * ea.x + ca1 * ea.y;
+  }
+  if (P.nvid > 0) sc += __ldg(Lp.vidk + (D.perm[sp] % P.nvid));
+  return sc;
+}
+
+// m_v = sum_e softmax_e(score_e) h_e over ALL in-edges of position p; a predecessor that is not in an earlier level
+// (col >= first position of this level) scores without its key term, keeps its softmax mass and adds a zero row (Q1)
+__device__ __forceinline__ void gather_row(const ClusterP& P, const CDir& D, const CLay& Lp, int p, long long q, int lstart, int lane,
+                                           const float (&wk)[8]) {
+  const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
+  const int ne = e1 - e0;
+  const int k0 = 8 * lane;
+  const int w4 = P.Hq;
+  const float* __restrict__ Hs = Lp.Hs;
+  const float ca0 = D.eattr ? __ldg(Lp.attnc) : 0.f, ca1 = D.eattr ? __ldg(Lp.attnc + 1) : 0.f;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = 0.f;
+  if (ne > 0 && ne <= 4) {
+    // ---- the common case: every predecessor row stays in registers between the score and the weighted sum
+    Row8 R[4];
+    float sc[4];
+    bool val[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      sc[t] = -INFINITY; val[t] = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
+      if (t < ne) {
+        const int sp = D.col[e0 + t];
+        val[t] = sp < lstart;
+        if (val[t]) load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
+        sc[t] = edge_terms(P, D, Lp, e0 + t, sp, ca0, ca1);
+      }
+    }
+    float dt[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < ne) { if (val[t]) sc[t] += dt[t]; mx = fmaxf(mx, sc[t]); }
+    }
+    float den = 0.f, ex[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { ex[t] = (t < ne) ? expf(sc[t] - mx) : 0.f; den += ex[t]; }
+    const float inv = 1.f / (den + 1e-16f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float a = val[t] ? ex[t] * inv : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaf(a, R[t].v[j], m[j]);
+    }
+  } else if (ne > 4) {
+    // ---- long in-edge lists: softmax statistics first (online), then the weighted rows; four rows in flight
+    float mx = -INFINITY, den = 0.f;
+    for (int eb = e0; eb < e1; eb += 4) {
+      Row8 R[4];
+      float sc[4], dt[4];
+      bool val[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        sc[t] = -INFINITY; val[t] = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
+        if (eb + t < e1) {
+          const int sp = D.col[eb + t];
+          val[t] = sp < lstart;
+          if (val[t]) load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
+          sc[t] = edge_terms(P, D, Lp, eb + t, sp, ca0, ca1);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
+      }
+      float bm = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (eb + t < e1) { if (val[t]) sc[t] += dt[t]; bm = fmaxf(bm, sc[t]); }
+      }
+      const float mnew = fmaxf(mx, bm);
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s += (eb + t < e1) ? expf(sc[t] - mnew) : 0.f;
+      den = den * expf(mx - mnew) + s;
+      mx = mnew;
+    }
+    const float inv = 1.f / (den + 1e-16f);
+    for (int eb = e0; eb < e1; eb += 4) {
+      Row8 R[4];
+      float sc[4], dt[4];
+      bool val[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        sc[t] = 0.f; val[t] = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
+        if (eb + t < e1) {
+          const int sp = D.col[eb + t];
+          val[t] = sp < lstart;
+          if (val[t]) {
+            load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
+            sc[t] = edge_terms(P, D, Lp, eb + t, sp, ca0, ca1);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float a = val[t] ? expf(sc[t] + dt[t] - mx) * inv : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaf(a, R[t].v[j], m[j]);
+      }
+    }
+  }
+  if (k0 < P.Kh) store_oprow(Lp.mimg, P.nckh, P.Q, q, lane, m);
+  float* mo = Lp.m32 + (size_t)p * P.ldh + k0;
+  if (k0 + 4 <= w4) *reinterpret_cast<float4*>(mo) = make_float4(m[0], m[1], m[2], m[3]);
+  if (k0 + 8 <= w4) *reinterpret_cast<float4*>(mo + 4) = make_float4(m[4], m[5], m[6], m[7]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_dev(const int* a, int n, int key) {      // first index with a[idx] >= key
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_constant__ ClusterP P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Wih = base;                                    // [plane][k chunk][96 rows x 128 B]
+  unsigned char* Ring = base + kWBytes;
+  CSmemTail& S = *reinterpret_cast<CSmemTail*>(Ring + (size_t)kCNStage * kCStageBytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_ctarank();
+  const int item = (int)cluster_idx();
+  const int g = item % P.G, di = item / P.G;
+  const int i = di / P.dirs, d = di - i * P.dirs;
+  const CDir& D = P.dir[d];
+  const CLay& Lp = P.lay[d][i];
+  const bool first_layer = i == 0, has_next = i + 1 < P.layers;
+  const int u0 = rank * P.U;
+  const int Kin = first_layer ? P.Kx : P.Kh;                   // padded width of the cell's input operand
+  const int nck_in = first_layer ? P.nckx : P.nckh;
+  unsigned char* inimg = first_layer ? P.ximg[d] : P.lay[d][i - 1].himg;
+
+  if (tid == 0) {
+    for (int s = 0; s < kCNStage; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.acc_full, 1);
+    mbar_init(&S.tmem_free, kCWorkWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tc::tmem_alloc(&S.tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_slot;
+
+  const bool ok = P.summary[2] == 0;           // schedule build flagged bad input: do nothing, the host raises
+  const int L = ok ? P.summary[0] : 0;
+  int4* tab = P.tab + (size_t)item * (P.max_levels + 1);
+
+  // ---- level table of this (direction, group): CTA 0 of the cluster builds it, the cluster barrier below publishes it
+  if (rank == 0 && L > 0) {
+    int gb_lo = 0, gb_hi = P.N;
+    if (P.G > 1) {
+      if (P.summary[3] != 0) {                  // level arrays with their own node ids: no order to cut groups by
+        if (g > 0) gb_lo = P.N;
+      } else {
+        const long long t0 = (long long)P.N * g / P.G, t1 = (long long)P.N * (g + 1) / P.G;
+        gb_lo = g == 0 ? 0 : P.gptr[lower_bound_dev(P.gptr, P.B + 1, (int)t0)];
+        gb_hi = g + 1 == P.G ? P.N : P.gptr[lower_bound_dev(P.gptr, P.B + 1, (int)t1)];
+      }
+    }
+    for (int l = tid; l < L; l += kCThreads) {
+      const int a = D.lvl_off[l], b = D.lvl_off[l + 1];
+      const int lo = a + lower_bound_dev(D.perm + a, b - a, gb_lo);
+      const int hi = a + lower_bound_dev(D.perm + a, b - a, gb_hi);
+      tab[l] = make_int4(lo, hi - lo, 0, a);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int run = ((gb_lo + 7) & ~7) + 8 * L * g;                // operand rows of a group start past every earlier group's
+      for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const int v = l < L ? (tab[l].y + 7) & ~7 : 0;
+        const int incl = warp_incl_scan(v, lane);
+        if (l < L) tab[l].z = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+  }
+
+  // ---- weights on chip: W_hh slice -> TMEM (hi tile, lo tile), W_ih slice -> shared memory, biases
+  if (warp < 4) {
+    const int gate = tid >> 5, uu = tid & 31, u = u0 + uu;
+    const bool live = gate < 3 && uu < P.U && u < P.H;
+    const int col = gate * P.Hq + u;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    const int nckw = P.HP >> 6;                                 // k chunks of the packed W_hh image (Kh64 / 64)
+    for (int ks = 0; ks < P.Kh / 16; ++ks) {
+      uint32_t wh[8], wl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { wh[j] = 0u; wl[j] = 0u; }
+      if (live) {
+        const uint4 h0 = packed_w8(Lp.w_hh, nckw, col, 2 * ks, 0), h1 = packed_w8(Lp.w_hh, nckw, col, 2 * ks + 1, 0);
+        const uint4 l0 = packed_w8(Lp.w_hh, nckw, col, 2 * ks, 1), l1 = packed_w8(Lp.w_hh, nckw, col, 2 * ks + 1, 1);
+        wh[0] = h0.x; wh[1] = h0.y; wh[2] = h0.z; wh[3] = h0.w; wh[4] = h1.x; wh[5] = h1.y; wh[6] = h1.z; wh[7] = h1.w;
+        wl[0] = l0.x; wl[1] = l0.y; wl[2] = l0.z; wl[3] = l0.w; wl[4] = l1.x; wl[5] = l1.y; wl[6] = l1.z; wl[7] = l1.w;
+      }
+      tc::st8(taddr + (uint32_t)(kColWhi + 8 * ks), wh);
+      tc::st8(taddr + (uint32_t)(kColWlo + 8 * ks), wl);
+    }
+    tc::wait_st();
+  } else {
+    const int t = tid - 128, nt = kCThreads - 128;
+    const int ngr = nck_in * 8;                                 // 16-byte granules per row
+    for (int idx = t; idx < 2 * kWRows * ngr; idx += nt) {
+      const int gk = idx % ngr, r = (idx / ngr) % kWRows, plane = idx / (ngr * kWRows);
+      const int gate = r >> 5, uu = r & 31, u = u0 + uu;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (uu < P.U && u < P.H && 8 * gk < Kin) w = packed_w8(Lp.w_ih, Lp.ih_nck, Lp.ih_col0 + gate * P.Hq + u, gk, plane);
+      *reinterpret_cast<uint4*>(Wih + ((size_t)plane * nck_in + (gk >> 3)) * kWChunkBytes + tc::tile_off(r, gk & 7)) = w;
+    }
+    for (int idx = t; idx < 4 * kCU; idx += nt) {
+      const int b = idx / kCU, uu = idx % kCU, u = u0 + uu;
+      S.bias[b][uu] = (uu < P.U && u < P.HP) ? __ldg(Lp.bias + (size_t)b * P.HP + u) : 0.f;
+    }
+  }
+  float wk[8];                                                  // key weights of the lane's k slice (gather phase)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wk[j] = (8 * lane + j < P.HP) ? __ldg(Lp.wk + 8 * lane + j) : 0.f;
+  tc::fence_async_smem();                // W_ih tiles were written with ordinary stores, the tensor core reads them
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  cluster_sync_all();
+
+  const uint32_t wih_s = smem_u32(Wih), ring_s = smem_u32(Ring);
+  uint32_t jring = 0, ct = 0;            // ring stages used so far, chunks done so far
+  const int gw = warp * kCS + rank;      // worker warp index in the cluster (rank-minor: a short level spreads over the CTAs)
+
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const int4 T = __ldcg(tab + l);
+    const int pos0 = T.x, n = T.y, q0 = T.z, lstart = T.w;
+    long long* tr = (P.trace && l < P.max_levels) ? P.trace + (((size_t)l * 256 + blockIdx.x) << 4) : nullptr;
+    if (tr && tid == 0) tr[0] = clock64();
+    if (n > 0) {
+      // ---------------- gather phase ----------------
+      const bool exchange = l > 0 || first_layer;
+      if (warp < kCWorkWarps) {
+        for (int r = gw; r < n; r += kCS * kCWorkWarps) {
+          if (first_layer) convert_x_row(P, D, d, pos0 + r, (long long)q0 + r, lane);
+          if (l > 0) gather_row(P, D, Lp, pos0 + r, (long long)q0 + r, lstart, lane, wk);
+        }
+      }
+      if (tr && tid == 0) tr[1] = clock64();
+      if (exchange) {
+        asm volatile("fence.proxy.async;" ::: "memory");        // operand rows: ordinary stores here, bulk copies (async proxy) there
+        cluster_sync_all();
+      }
+      if (tr && tid == 0) tr[2] = clock64();
+      // ---------------- projection + cell ----------------
+#pragma unroll 1
+      for (int r0 = 0; r0 < n; r0 += kRC) {
+        const int rows = min(kRC, n - r0);
+        const uint32_t bytes = (uint32_t)((rows + 7) & ~7) * tc::ROW_BYTES;
+        const int ns = nck_in + (l > 0 ? P.nckh : 0);           // stages of this chunk: input operand chunks, then aggregate chunks
+        if (warp == kCWorkWarps) {
+          // ---- issuer warp (converged; one elected lane issues)
+          if (!first_layer && r0 == 0) {
+            const unsigned int* fl = P.flags + (item - P.dirs * P.G);       // cluster (i - 1, d, g)
+            while (ld_acquire_u32(fl) < (unsigned int)(l + 1)) {}
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          const uint32_t idesc = uni(tc::instr_desc_f16(128, (rows + 15) & ~15));
+          auto load_stage = [&](int k) {
+            const uint32_t j = jring + (uint32_t)k, st = j % kCNStage, use = j / kCNStage;
+            if (use >= 1) mbar_wait(&S.empty[st], (use - 1) & 1u);
+            if (elect_one()) {
+              const bool is_in = k < nck_in;
+              const int c = is_in ? k : k - nck_in;
+              unsigned char* img = is_in ? inimg : Lp.mimg;
+              const int nck = is_in ? nck_in : P.nckh;
+              const unsigned char* src_hi = img + ((((size_t)0 * nck + c) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
+              const unsigned char* src_lo = img + ((((size_t)1 * nck + c) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
+              unsigned char* dst = Ring + (size_t)st * kCStageBytes;
+              mbar_expect_tx(&S.full[st], 2 * bytes);
+              bulk_g2s(dst, src_hi, bytes, &S.full[st]);
+              bulk_g2s(dst + kRC * tc::ROW_BYTES, src_lo, bytes, &S.full[st]);
+            }
+            __syncwarp();
+          };
+          for (int k = 0; k < min(2, ns); ++k) load_stage(k);
+#pragma unroll 1
+          for (int k = 0; k < ns; ++k) {
+            const uint32_t j = jring + (uint32_t)k, st = j % kCNStage, use = j / kCNStage;
+            mbar_wait(&S.full[st], use & 1u);
+            if (k == 0 && ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);   // the previous chunk's accumulators have been read
+            tc::fence_after_sync();
+            const bool is_in = k < nck_in;
+            const int c = is_in ? k : k - nck_in;
+            const int Kop = is_in ? Kin : P.Kh;
+            const int nks = min(4, (Kop - 64 * c) >> 4);
+            const uint32_t sb = uni(ring_s + st * (uint32_t)kCStageBytes);
+            const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)(kRC * tc::ROW_BYTES));
+            if (is_in) {
+              const uint32_t a0 = uni(wih_s + (uint32_t)c * kWChunkBytes), a1 = uni(wih_s + (uint32_t)(nck_in + c) * kWChunkBytes);
+              const uint64_t ah = tc::smem_desc(a0), al = tc::smem_desc(a1);
+              const uint32_t acc = uni(tmem + (uint32_t)kColAccX);
+              if (elect_one()) {
+                for (int ks = 0; ks < nks; ++ks) {
+                  tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+                  tc::mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
+                  tc::mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1u);
+                }
+              }
+            } else {
+              const uint32_t acc = uni(tmem + (uint32_t)kColAccH);
+              const uint32_t ah = uni(tmem + (uint32_t)(kColWhi + 32 * c)), al = uni(tmem + (uint32_t)(kColWlo + 32 * c));
+              if (elect_one()) {
+                for (int ks = 0; ks < nks; ++ks) {
+                  tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+                  tc::mma_f16_ts(acc, ah + 8 * ks, bl + 2 * ks, idesc, 1u);
+                  tc::mma_f16_ts(acc, al + 8 * ks, bh + 2 * ks, idesc, 1u);
+                }
+              }
+            }
+            if (elect_one()) tc::commit(&S.empty[st]);
+            __syncwarp();
+            if (k + 2 < ns) load_stage(k + 2);
+          }
+          if (elect_one()) tc::commit(&S.acc_full);
+          __syncwarp();
+        } else {
+          // ---- worker warps: epilogue. TMEM lane = gate * 32 + unit, column = row of the chunk.
+          mbar_wait(&S.acc_full, ct & 1u);
+          tc::fence_after_sync();
+          const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
+          const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
+          const int u = u0 + 4 * ug;
+#pragma unroll 1
+          for (int s0 = 0; s0 < rows; s0 += kSub) {
+            if (qd < 3) {
+              float v[32];
+              if (acc_id == 0 || l > 0) {
+                tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)((acc_id ? kColAccH : kColAccX) + s0), v);
+                tc::wait_ld();
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;         // level 0: hidden state 0, nothing was projected
+              }
+              float* dst = &S.stage[acc_id][32 * qd + lane][0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[j] = v[j];
+            }
+            workers_sync();
+            const int rr = s0 + row;
+            if (rr < rows && 4 * ug < P.U) {
+              const int p = pos0 + r0 + rr;
+              float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+              const bool in_row = u + 4 <= P.Hq;
+              if (l > 0 && in_row) mv = ldcg4(Lp.m32 + (size_t)p * P.ldh + u);
+              float o[4];
+              const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int uu = 4 * ug + k;
+                const float xr = S.stage[0][uu][row], xz = S.stage[0][32 + uu][row], xn = S.stage[0][64 + uu][row];
+                const float hr = S.stage[1][uu][row], hz = S.stage[1][32 + uu][row], hn = S.stage[1][64 + uu][row];
+                const float rg = fast_sigmoid(xr + hr + S.bias[0][uu]);
+                const float zg = fast_sigmoid(xz + hz + S.bias[1][uu]);
+                const float ng = fast_tanh(xn + S.bias[2][uu] + rg * (hn + S.bias[3][uu]));
+                o[k] = ng + zg * (mm[k] - ng);
+              }
+              if (in_row) *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
+              if (has_next && u < P.Kh) {
+                uint32_t h0, h1, l0, l1;
+                tc::split2(o[0], o[1], h0, l0);
+                tc::split2(o[2], o[3], h1, l1);
+                const long long q = (long long)q0 + r0 + rr;
+                unsigned char* ph = oprow_ptr(Lp.himg, 0, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+                unsigned char* pl = oprow_ptr(Lp.himg, 1, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+                *reinterpret_cast<uint2*>(ph) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
+              }
+            }
+            workers_sync();
+          }
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.tmem_free);
+        }
+        jring += (uint32_t)ns;
+        ct += 1;
+      }
+      if (tr && tid == 0) tr[3] = clock64();
+      // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
+      asm volatile("fence.proxy.async;" ::: "memory");
+      cluster_sync_all();
+      if (tr && tid == 0) tr[4] = clock64();
+    }
+    if (has_next && rank == 0 && tid == 0) st_release_u32(P.flags + item, (unsigned int)(l + 1));
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace dagnn
+
+using namespace dagnn;
+
+static size_t calign256(size_t x) { return (x + 255) / 256 * 256; }
+
+namespace dagnn {
+
+// rows of an operand-row plane: every (group, level) segment starts on a multiple of 8 rows, groups are spaced by 8 L rows
+static int64_t cluster_q_rows(int64_t N, int32_t max_levels, int dirs, int layers) {
+  const int gcap = kCMaxItems / (dirs * layers) > 0 ? kCMaxItems / (dirs * layers) : 1;
+  return N + 8 * (int64_t)max_levels * gcap + 64;
+}
+
+bool cluster_path_supported(int dirs, int layers, int Din, int H, int nvid) {
+  (void)nvid;
+  return H >= 1 && H <= kCMaxH && Din >= 1 && Din <= kCMaxH && dirs * layers <= kCMaxItems;
+}
+
+size_t cluster_workspace_bytes(int dirs, int layers, int Din, int H, int64_t N, int32_t max_levels) {
+  if (!cluster_path_supported(dirs, layers, Din, H, 0)) return 0;
+  const int64_t Q = cluster_q_rows(N, max_levels, dirs, layers);
+  const int nckh = (H + 63) / 64, nckx = (Din + 63) / 64;
+  const size_t plane_h = calign256((size_t)2 * nckh * Q * 128), plane_x = calign256((size_t)2 * nckx * Q * 128);
+  const size_t ldh = (size_t)round_up(H, 4);
+  size_t b = 1024;                                                          // flags
+  b += calign256((size_t)kCMaxItems * (max_levels + 1) * sizeof(int4));     // level tables
+  b += (size_t)dirs * plane_x;                                              // X operand rows per direction
+  b += (size_t)dirs * layers * (2 * plane_h + calign256((size_t)N * ldh * sizeof(float)));   // h rows, m rows, m fp32
+  return b + 1024;
+}
+
+static int g_cluster_max[kMaxDevices] = {0};       // resident 8-CTA clusters of k_sweep_cluster per device (0 = path unavailable)
+
+int cluster_forward(const DagnnSweepArgs* A, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const DagnnSchedule* S = A->sched;
+  const int dirs = S->dirs, layers = A->num_layers, H = A->H;
+  if (!cluster_path_supported(dirs, layers, A->Din, H, A->nvid)) return DAGNN_OK;
+  static PerDeviceOnce once;
+  int dev = 0;
+  if (int rc = per_device_once(once, &dev, [&](int dv) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
+        if (e != cudaSuccess) { cudaGetLastError(); g_cluster_max[dv] = 0; return (int)DAGNN_OK; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kCS * 32); cfg.blockDim = dim3(kCThreads); cfg.dynamicSmemBytes = kCSmemBytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kCS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        e = cudaOccupancyMaxActiveClusters(&nc, k_sweep_cluster, &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        g_cluster_max[dv] = nc > kCMaxItems ? kCMaxItems : nc;
+        return (int)DAGNN_OK;
+      }))
+    return rc;
+  const int items = dirs * layers;
+  const int cmax = g_cluster_max[dev];
+  if (cmax < items) return DAGNN_OK;                 // not enough resident clusters for the layer pipeline: grid-wide sweep
+  int G = cmax / items;
+  if (S->B < 1 || !S->gptr) G = 1;
+  if (G > S->B && S->B >= 1) G = (int)S->B;
+  if (G < 1) G = 1;
+
+  ClusterP P;
+  memset(&P, 0, sizeof(P));
+  DagnnPackLayout lay[DAGNN_MAX_LAYERS];
+  for (int i = 0; i < layers; ++i)
+    if (int rc = dagnn_pack_layout(i == 0 ? A->Din : H, H, A->nvid, i == 0, i + 1 == layers, &lay[i])) return rc;
+  P.dirs = dirs; P.layers = layers; P.G = G; P.H = H; P.Hq = lay[0].Hq; P.Mc = lay[0].Mc; P.HP = lay[0].HP; P.nvid = A->nvid;
+  P.use_ea = A->use_edge_attr; P.Din = A->Din; P.N = (int)S->N; P.B = (int)S->B;
+  P.U = round_up(ceil_div(H, kCS), 4);
+  P.Kh = round_up(H, 16); P.Kx = round_up(A->Din, 16);
+  P.nckh = ceil_div(P.Kh, 64); P.nckx = ceil_div(P.Kx, 64);
+  P.vec_x = ((A->ldx & 3) == 0 && (A->Din & 3) == 0 && ((uintptr_t)A->X & 15) == 0) ? 1 : 0;
+  P.max_levels = S->max_levels;
+  P.ldh = A->ldh; P.ldx = A->ldx; P.Q = cluster_q_rows(S->N, S->max_levels, dirs, layers);
+  P.X = A->X; P.summary = S->summary; P.gptr = S->gptr;
+  P.trace = static_cast<long long*>(A->trace);
+  char* ws = static_cast<char*>(A->workspace);
+  P.flags = reinterpret_cast<unsigned int*>(ws); ws += 1024;
+  P.tab = reinterpret_cast<int4*>(ws); ws += calign256((size_t)kCMaxItems * (S->max_levels + 1) * sizeof(int4));
+  const size_t plane_h = calign256((size_t)2 * P.nckh * P.Q * 128), plane_x = calign256((size_t)2 * P.nckx * P.Q * 128);
+  const size_t m32_bytes = calign256((size_t)S->N * A->ldh * sizeof(float));
+  for (int d = 0; d < dirs; ++d) { P.ximg[d] = reinterpret_cast<unsigned char*>(ws); ws += plane_x; }
+  for (int d = 0; d < dirs; ++d) {
+    P.dir[d].perm = S->perm[d]; P.dir[d].rowptr = S->rowptr[d]; P.dir[d].col = S->col[d];
+    P.dir[d].eattr = A->use_edge_attr ? S->eattr[d] : nullptr; P.dir[d].lvl_off = S->lvl_off[d];
+    for (int i = 0; i < layers; ++i) {
+      const DagnnPackLayout& Lz = lay[i];
+      const float* pk = A->packed[d][i];
+      CLay& q = P.lay[d][i];
+      q.Hs = A->Hs[d][i]; q.bias = pk + Lz.bias_off; q.wk = pk + Lz.wk_off; q.attnc = pk + Lz.attnc_off; q.vidk = pk + Lz.vidk_off;
+      q.w_hh = reinterpret_cast<const __half*>(pk + Lz.imgh_off);
+      if (i == 0) {
+        q.w_ih = reinterpret_cast<const __half*>(pk + Lz.imgx_off); q.ih_col0 = 0; q.ih_nck = Lz.Kin64 / 64;
+      } else {                                       // W_ih of layer i rides behind W_hh of layer i - 1 (pack.cu)
+        q.w_ih = reinterpret_cast<const __half*>(A->packed[d][i - 1] + lay[i - 1].imgh_off); q.ih_col0 = Lz.Mc; q.ih_nck = Lz.Kh64 / 64;
+      }
+      q.himg = reinterpret_cast<unsigned char*>(ws); ws += plane_h;
+      q.mimg = reinterpret_cast<unsigned char*>(ws); ws += plane_h;
+      q.m32 = reinterpret_cast<float*>(ws); ws += m32_bytes;
+    }
+  }
+  if ((size_t)(ws - static_cast<char*>(A->workspace)) > A->workspace_bytes)
+    return set_err(DAGNN_E_WORKSPACE, "sweep: workspace too small (dagnn_sweep_workspace_bytes)");
+  DAGNN_CUDA_OK(cudaMemsetAsync(A->workspace, 0, 1024, st));       // level counters
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCS * items * G); cfg.blockDim = dim3(kCThreads); cfg.dynamicSmemBytes = kCSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kCS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DAGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sweep_cluster, P));
+  *handled = true;
+  return check_launch("k_sweep_cluster");
+}
+
+}  // namespace dagnn

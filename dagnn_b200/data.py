@@ -354,6 +354,32 @@ def shard_graph_ranges(nodes_per_graph: Sequence[int], world_size: int) -> List[
     return out
 
 
+def shard_graph_ids(nodes_per_graph: Sequence[int], world_size: int, depths: Optional[Sequence[int]] = None,
+                    level_cost_nodes: float = 100.0) -> List[np.ndarray]:
+    """Graph ids of every shard. Without `depths`: the reference's contiguous node-balanced rule (`shard_graph_ranges`).
+    With `depths` (levels of every graph): depth-aware balance. The sweep walks the levels of a shard one after the other, so
+    a shard costs about  levels * t_level + nodes * t_node  — the deepest graph of a shard sets the first term (measured:
+    SCALE_r01.json, 97 levels on one rank against 66 on rank 0 cost 21 % at equal node counts). Graphs are dealt in order of
+    decreasing depth, each to the shard whose modelled cost  level_cost_nodes * max depth + nodes  stays smallest: the deepest
+    graphs land on different shards and a shard with a deep graph gets fewer nodes. Ids inside a shard are ascending.
+    Shards may be empty when there are fewer graphs than ranks."""
+    cnt = np.asarray(nodes_per_graph, dtype=np.int64)
+    if depths is None:
+        return [np.arange(r.start, r.stop, dtype=np.int64) for r in shard_graph_ranges(cnt, world_size)]
+    dep = np.asarray(depths, dtype=np.int64)
+    order = np.lexsort((np.arange(len(cnt)), -cnt, -dep))            # depth desc, then nodes desc, then id
+    nodes = np.zeros(world_size, dtype=np.int64)
+    deep = np.zeros(world_size, dtype=np.int64)
+    out = [[] for _ in range(world_size)]
+    for gidx in order:
+        cost = level_cost_nodes * np.maximum(deep, dep[gidx]) + nodes + cnt[gidx]
+        r = int(np.argmin(cost))
+        out[r].append(int(gidx))
+        nodes[r] += cnt[gidx]
+        deep[r] = max(deep[r], dep[gidx])
+    return [np.asarray(sorted(ids), dtype=np.int64) for ids in out]
+
+
 def deterministic_init_(module: torch.nn.Module, seed: int) -> torch.nn.Module:
     """Fill every parameter from a numpy generator (platform/torch-version independent), with the scale of
     the default initialisers: embeddings ~ N(0,1), everything else ~ U(-1/sqrt(fan), 1/sqrt(fan)) where fan is
@@ -385,6 +411,15 @@ def deterministic_init_(module: torch.nn.Module, seed: int) -> torch.nn.Module:
 def graph_node_counts(B: DagBatch) -> np.ndarray:
     ng = int(getattr(B, "num_graphs", int(B.batch.max()) + 1))
     return np.bincount(B.batch.numpy(), minlength=ng)
+
+
+def graph_depths(B: DagBatch) -> np.ndarray:
+    """Number of levels of every graph of a batch (max forward level + 1)."""
+    lvl = (B._bi_layer_idx0 if hasattr(B, "_bi_layer_idx0") else B.bi_layer_index[0][0]).numpy()
+    cnt = graph_node_counts(B)
+    out = np.zeros(len(cnt), dtype=np.int64)
+    np.maximum.at(out, B.batch.numpy(), lvl + 1)
+    return out
 
 
 def select_graphs(B: DagBatch, graph_ids) -> DagBatch:
@@ -430,6 +465,8 @@ def split_batch(B: DagBatch, ranges) -> List[DagBatch]:
     return [select_graphs(B, r) for r in ranges]
 
 
-def shard_batch(B: DagBatch, world_size: int) -> List[DagBatch]:
-    """Node-balanced contiguous graph shards, one per rank (rule of ogbg-code/tg/dataloader.py:17-27)."""
-    return split_batch(B, shard_graph_ranges(graph_node_counts(B), world_size))
+def shard_batch(B: DagBatch, world_size: int, depth_aware: bool = True) -> List[DagBatch]:
+    """One shard per rank: depth-aware balance (`shard_graph_ids`), or with depth_aware=False the contiguous node-balanced rule
+    of ogbg-code/tg/dataloader.py:17-27. Empty shards come back as None (the reference collater drops them)."""
+    ids = shard_graph_ids(graph_node_counts(B), world_size, graph_depths(B) if depth_aware else None)
+    return [select_graphs(B, r) if len(r) else None for r in ids]

@@ -58,8 +58,10 @@ def embed(x: torch.Tensor, depth: torch.Tensor, type_tab, attr_tab, depth_tab, m
         img = torch.empty(nb + 1024, device=x.device, dtype=torch.uint8)
         off = (-img.data_ptr()) % 1024
         img = img[off: off + nb]
-    check(lib().dagnn_embed_f32(_ptr(x), _ptr(depth), _ptr(T), _ptr(A), _ptr(P), int(max_depth), N, D, _ptr(X), D,
-                                _ptr(img), _stream()), "dagnn_embed_f32")
+    if P.shape[0] != int(max_depth) + 1:
+        raise _lib.DagnnError("depth table has %d rows, max_depth + 1 = %d expected" % (P.shape[0], int(max_depth) + 1))
+    check(lib().dagnn_embed_f32(_ptr(x), _ptr(depth), _ptr(T), _ptr(A), _ptr(P), int(max_depth), int(T.shape[0]), int(A.shape[0]),
+                                N, D, _ptr(X), D, _ptr(img), _stream()), "dagnn_embed_f32")
     X._dagnn_image = img
     return X
 

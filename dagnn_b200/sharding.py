@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .data import DagBatch, graph_node_counts, select_graphs, shard_graph_ranges
+from .data import DagBatch, graph_depths, graph_node_counts, select_graphs, shard_graph_ids
 
 
 def rank_world(group=None):
@@ -24,14 +24,25 @@ def rank_world(group=None):
     return 0, 1
 
 
-def shard_for_rank(B: DagBatch, rank: Optional[int] = None, world_size: Optional[int] = None):
-    """-> (sub-batch of this rank, range of global graph ids it owns). Every rank computes the same partition
-    from the node counts (deterministic, no communication)."""
+def shard_for_rank(B: DagBatch, rank: Optional[int] = None, world_size: Optional[int] = None, depth_aware: bool = True):
+    """-> (sub-batch of this rank or None when the rank owns no graph, ascending global graph ids it owns). Every rank
+    computes the same partition from the node counts and graph depths (deterministic, no communication): depth-aware by
+    default (`data.shard_graph_ids`: the deepest graphs go to different ranks and take fewer nodes with them), the reference's
+    contiguous node-balanced rule (ogbg-code/tg/dataloader.py:17-27) with depth_aware=False."""
     r, w = rank_world()
     rank = r if rank is None else rank
     world_size = w if world_size is None else world_size
-    ranges = shard_graph_ranges(graph_node_counts(B), world_size)
-    return select_graphs(B, ranges[rank]), ranges[rank]
+    ids = shard_graph_ids(graph_node_counts(B), world_size, graph_depths(B) if depth_aware else None)
+    mine = ids[rank]
+    return (select_graphs(B, mine) if len(mine) else None), mine
+
+
+def unshard_rows(rows: torch.Tensor, ids_per_rank: Sequence[Sequence[int]]) -> torch.Tensor:
+    """Rows gathered in rank order (`gather_rows`) -> rows in global graph order."""
+    order = torch.as_tensor(np.concatenate([np.asarray(i, dtype=np.int64) for i in ids_per_rank]), device=rows.device)
+    out = torch.empty_like(rows)
+    out[order] = rows
+    return out
 
 
 def gather_rows(local: torch.Tensor, rows_per_rank: Sequence[int], group=None) -> torch.Tensor:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 6
+#define DAGNN_ABI_VERSION 7
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -50,15 +50,17 @@ int64_t dagnn_launch_count(void);
  * Node encoder:  X[v,:] = T[x[v,0],:] + A[x[v,1],:] + P[min(depth[v], max_depth),:]
  * replaces ASTNodeEncoder.forward, ogbg-code/utils.py:26-28 (called at ogbg-code/model/dagnn.py:139).
  * x int64 [N,2] row-major, depth int64 [N]; tables fp32 row-major with leading dimension D; X fp32 [N, ldx].
- * Unlike the reference it does not clamp `depth` in place.
+ * Unlike the reference it does not clamp `depth` in place. n_types / n_attrs = rows of the two tables: a row whose index
+ * is outside its table (nn.Embedding raises IndexError there) or whose depth is negative becomes NaN — no out-of-bounds
+ * read, and every output depending on it is NaN.
  * x_image (optional, NULL = off): a second copy of X as fp16 hi / lo halves in the tcgen05 operand-image layout
  * (128-node tiles x 64-wide k chunks, dagnn_operand_image_bytes(N, D) bytes, 1024-byte aligned; needs D % 4 == 0) that
  * dagnn_sweep_forward_f32 can bulk-copy for its first projection (DagnnSweepArgs.X_image).
  * --------------------------------------------------------------------------------------------------------- */
 size_t dagnn_operand_image_bytes(int64_t N, int32_t D);
 int dagnn_embed_f32(const int64_t* x, const int64_t* depth, const float* type_tab, const float* attr_tab,
-                    const float* depth_tab, int max_depth, int64_t N, int D, float* X, int64_t ldx, void* x_image,
-                    void* stream);
+                    const float* depth_tab, int max_depth, int64_t n_types, int64_t n_attrs, int64_t N, int D, float* X,
+                    int64_t ldx, void* x_image, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Integer pre-pass (bit-exact): level-sorted node order + in-edge CSR per direction.
@@ -83,7 +85,8 @@ typedef struct DagnnSchedule {
   float* eattr[DAGNN_MAX_DIRS];     /* [E,2] edge_attr rows in CSR order, or NULL              */
   int32_t* gptr;                    /* [B+1] first node id of each graph (batch vector sorted) */
   /* summary[0]=num_levels of dir 0, [1]=num_levels of dir 1, [2]=status (0 ok, 1 level >= max_levels,
-   * 2 node id / edge endpoint out of range), [3..7] reserved.                                       */
+   * 2 node id / edge endpoint out of range), [3] = 1 when a level array carries node ids other than 0..N-1 in order
+   * (positions inside a level are then not sorted by node id), [4..7] reserved.                       */
   int32_t* summary;                 /* [8]                                                     */
 } DagnnSchedule;
 
@@ -220,11 +223,14 @@ typedef struct DagnnReadoutBlock {
 int dagnn_readout_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* blocks, int32_t nblocks, int32_t pool,
                       float* out, int64_t ldo, void* stream);
 
-/* Diagnostic: C[M,N] = A[M,K] * B[N,K]^T (fp32 row-major) through the same tcgen05 3xTF32 building blocks the level
- * kernel uses (K-major SWIZZLE_128B operand tiles, TMEM accumulators). N % 16 == 0, 16 <= N <= 256, K % 32 == 0. */
-int dagnn_tc_selftest_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
-/* The same in the fp16 x 3 split (hi*hi + lo*hi + hi*lo on kind::f16, K = 16 per MMA) the level kernel runs. K % 64 == 0. */
+/* Diagnostics of the tcgen05 building blocks the level kernels use (K-major SWIZZLE_128B operand tiles, fp16 x 3 split on
+ * kind::f16, TMEM accumulators), fp32 row-major in and out:
+ *   f16x3: C[M,N] = A[M,K] * B[N,K]^T, both operands from shared memory. N % 16 == 0, 16 <= N <= 256, K % 64 == 0.
+ *   ts   : C[N,R] = X[N,K] * W[R,K]^T with W resident in TMEM as the A operand (hi rows on lanes 0..63, lo rows on lanes
+ *          64..127) and the rows of X as the shared-memory B operand — the arrangement of the cluster sweep.
+ *          R <= 64, N % 16 == 0, 16 <= N <= 256, K % 16 == 0, K <= 256. */
 int dagnn_tc_selftest_f16x3(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+int dagnn_tc_selftest_ts(const float* W, const float* X, float* C, int32_t R, int32_t N, int32_t K, void* stream);
 
 /* Un-permute states for inspection / tests: dst[v,:] = src[pos[dir][v],:]  (fp32 [N,H]) */
 int dagnn_states_to_node_order_f32(const DagnnSchedule* sched, int32_t dir, const float* src, int64_t lds,

@@ -64,6 +64,28 @@ def test_dvae_row_decoders():
     assert Gb.x.shape == (40, 10)
 
 
+def test_depth_aware_sharding_spreads_deep_graphs_and_balances_modelled_cost():
+    """data.shard_graph_ids with depths: the w deepest graphs land on w different shards, every graph is owned exactly once,
+    and the modelled cost (level_cost_nodes * max depth + nodes) is flatter than under the contiguous node-balanced rule."""
+    B = D.make_code2_batch(64, 20262)
+    cnt, dep = D.graph_node_counts(B), D.graph_depths(B)
+    assert dep.shape == cnt.shape and int(dep.max()) == int(B._bi_layer_idx0.max()) + 1
+    for w in (2, 4, 8):
+        ids = D.shard_graph_ids(cnt, w, dep)
+        assert sorted(int(g) for r in ids for g in r) == list(range(64))
+        deepest = np.argsort(-dep, kind="stable")[:w]
+        owners = {k for k, r in enumerate(ids) for g in deepest if g in set(r.tolist())}
+        assert len(owners) == w
+        cost = lambda shard: 100.0 * dep[shard].max() + cnt[shard].sum()
+        flat = [cost(r) for r in ids]
+        ref = [cost(r) for r in D.shard_graph_ids(cnt, w) if len(r)]
+        assert max(flat) <= max(ref) + 1e-9
+    # fewer graphs than ranks: empty shards are allowed and come back as None from shard_batch
+    tiny = D.make_code2_batch(2, 3)
+    parts = D.shard_batch(tiny, 4)
+    assert sum(p is not None for p in parts) == 2 and sum(p.num_graphs for p in parts if p is not None) == 2
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -89,7 +111,9 @@ def _worker(rank, world, port, out):
                                                                                     b._bi_layer_idx0.float()], 1))
         full = per_graph(B)
         got = sharding.gather_rows(per_graph(mine), [int(s[0]) for s in allsz])
-        assert torch.equal(got, full)
+        all_ids = [D.shard_graph_ids(D.graph_node_counts(B), world, D.graph_depths(B))[r] for r in range(world)]
+        assert np.array_equal(np.asarray(rng), all_ids[rank])
+        assert torch.equal(sharding.unshard_rows(got, all_ids), full)
         # (3) gradient all-reduce: sum of shard gradients of a sum-loss == full-batch gradient
         torch.manual_seed(0)
         lin = torch.nn.Linear(3, 2)
