@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ Readout
         const int c = lane + 32 * j;
         if (c0 + c < b.width) {
           const float h = __ldcg(srow + c);
-          acc[j] = is_max ? fmaxf(acc[j], h) : acc[j] + h;
+          acc[j] = is_max ? ((h > acc[j] || h != h) ? h : acc[j]) : acc[j] + h;     // max keeps a NaN (fmaxf would drop it)
         }
       }
     }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ Readout
     int n = pcnt[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) {
-      r = is_max ? fmaxf(r, part[w][c]) : r + part[w][c];
+      r = is_max ? ((part[w][c] > r || part[w][c] != part[w][c]) ? part[w][c] : r) : r + part[w][c];
       n += pcnt[w];
     }
     if (n == 0) r = 0.f;

@@ -987,8 +987,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const __grid_constant__ S
   __syncthreads();
 
   // gate phase of step s (s >= 0), then proj phase s (s = -1: X)
+  // (a schedule flagged unusable runs nothing at all — not even the projection of X: its tables were never built)
 #pragma unroll 1
-  for (int s = -1; s < nsteps; ++s) {
+  for (int s = nsteps > 0 ? -1 : 0; s < nsteps; ++s) {
     long long* tr = P.trace ? P.trace + ((size_t)(s + 1) * 256 + blockIdx.x) * 16 : nullptr;
     if (tr && tid == 0) { tr[0] = clock64(); tr[1] = tr[2] = tr[3] = 0; tr[8] = tr[9] = 0; }
     if (s >= 0) {

@@ -40,7 +40,8 @@ constexpr int kCMaxH = 256;                        // K of an operand row: 4 chu
 constexpr int kCU = kCMaxH / kCS;                  // hidden units per CTA at most (3 * 32 = 96 TMEM lanes)
 constexpr int kRC = 128;                           // rows per projection chunk (N of the MMAs)
 constexpr int kCStageBytes = 2 * kRC * tc::ROW_BYTES;      // hi + lo tile of 128 rows x 64 k = 32 KB
-constexpr int kCNStage = 3;
+constexpr int kCSlots = 12;                        // operand slots of 8 KB (hi + lo tile of 32 rows x 64 k)
+constexpr int kCRingBytes = 3 * kCStageBytes;      // 96 KB operand region
 constexpr int kWRows = 96;                         // W_ih slice rows: gate * 32 + unit
 constexpr int kWChunkBytes = kWRows * tc::ROW_BYTES;       // 12 KB per (plane, k chunk)
 constexpr int kWBytes = 2 * 4 * kWChunkBytes;              // 96 KB
@@ -81,7 +82,7 @@ struct ClusterP {
   const int* summary;          // [0] levels, [2] status, [3] node ids are not the identity
   const int* gptr;             // [B+1]
   int4* tab;                   // [items][max_levels + 1] per level: first position, rows, first operand row, level start
-  unsigned int* flags;         // [items] levels published
+  unsigned int* flags;         // [items][8] projection chunks whose states each CTA of the cluster has published
   long long* trace;            // optional [levels][256][16] clock64 stamps per (level, CTA): 0 start, 1 gathered, 2 exchanged,
                                // 3 projected + cells done, 4 level closed
   CDir dir[DAGNN_MAX_DIRS];
@@ -91,10 +92,13 @@ struct ClusterP {
 struct CSmemTail {
   float stage[2][kWRows][kSLd];     // epilogue transpose: [accumulator][gate * 32 + unit][row of the pass]
   float bias[4][kCU];
-  uint64_t full[kCNStage], empty[kCNStage], acc_full, tmem_free;
+  uint64_t full[kCSlots], empty[kCSlots], acc_full, tmem_free;
   uint32_t tmem_slot;
+  int nlong;                        // gather phase: rows of this CTA with long in-edge lists (index into the level)
+  int longrow[32];
 };
-constexpr size_t kCSmemBytes = 1024 + (size_t)kWBytes + (size_t)kCNStage * kCStageBytes + sizeof(CSmemTail);
+static_assert(sizeof(float) * 2 * kWRows * kSLd >= sizeof(float) * 16 * 260, "the half-warp partials alias the epilogue stage");
+constexpr size_t kCSmemBytes = 1024 + (size_t)kWBytes + (size_t)kCRingBytes + sizeof(CSmemTail);
 static_assert(kCSmemBytes <= 232448, "shared memory plan exceeds the 227 KB opt-in limit");
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -122,46 +126,87 @@ __device__ __forceinline__ uint4 packed_w8(const __half* img, int nck, int col, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// gather phase: one warp per node. Lane l owns k = [8 l, 8 l + 8) of a row.
+// gather phase: HALF a warp per node (two nodes per warp in lockstep). Lane hl = lane & 15 owns k = [16 hl, 16 hl + 16) of a
+// row. A node costs its chain of dependent L2 round trips (row pointers -> in-edge list -> predecessor rows), so up to four
+// predecessor rows per node are in flight at once and the softmax is ONLINE (running max / denominator / weighted sum,
+// rescaled when the max moves): one pass over the in-edge list whatever its length. Lists longer than kLongEdges are split
+// over the 16 half-warps of the CTA and merged through shared memory.
 // ------------------------------------------------------------------------------------------------------------
-struct Row8 { float v[8]; };
+constexpr int kLongEdges = 16;
+constexpr int kMaxLong = 32;       // long lists per CTA and level that get the cooperative treatment (more: a half-warp alone)
+constexpr int kPartLd = 260;       // floats per half-warp partial: 256 weighted sums, running max, denominator
 
-__device__ __forceinline__ void load_row8(Row8& R, const float* __restrict__ row, int k0, int width4) {
-  // width4 = valid floats of the row rounded up to 4 (rows are zero padded to it)
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  if (k0 + 4 <= width4) a = ldcg4(row + k0);
-  if (k0 + 8 <= width4) b = ldcg4(row + k0 + 4);
-  R.v[0] = a.x; R.v[1] = a.y; R.v[2] = a.z; R.v[3] = a.w; R.v[4] = b.x; R.v[5] = b.y; R.v[6] = b.z; R.v[7] = b.w;
+struct Row16 { float4 v[4]; };
+struct GAcc {
+  float mx, den;
+  float4 m[4];
+};
+
+// max that keeps a NaN (fmaxf drops it): a non-finite predecessor state must poison the aggregate, not vanish from it
+__device__ __forceinline__ float nanmax(float a, float b) { return (b > a || b != b) ? b : a; }
+__device__ __forceinline__ float half_sum(float v) {             // sum over the 16 lanes of a half-warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-__device__ __forceinline__ float dot8(const Row8& R, const float (&w)[8]) {
+__device__ __forceinline__ void load_row16(Row16& R, const float* __restrict__ row, int k0, int width4, bool on) {
+  // width4 = valid floats of the row rounded up to 4 (rows are zero padded to it)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    R.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on && k0 + 4 * j + 4 <= width4) R.v[j] = ldcg4(row + k0 + 4 * j);
+  }
+}
+__device__ __forceinline__ float dot16(const Row16& R, const float4 (&w)[4]) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s = fmaf(R.v[j], w[j], s);
+  for (int j = 0; j < 4; ++j) {
+    s = fmaf(R.v[j].x, w[j].x, s); s = fmaf(R.v[j].y, w[j].y, s); s = fmaf(R.v[j].z, w[j].z, s); s = fmaf(R.v[j].w, w[j].w, s);
+  }
   return s;
 }
-__device__ __forceinline__ void store_oprow(unsigned char* img, int nck, long long Q, long long q, int lane, const float (&v)[8]) {
-  uint4 hi, lo;
-  tc::split8(v, hi, lo);
-  *reinterpret_cast<uint4*>(oprow_ptr(img, 0, nck, Q, q, lane)) = hi;
-  *reinterpret_cast<uint4*>(oprow_ptr(img, 1, nck, Q, q, lane)) = lo;
+// 16 consecutive k of operand row q, owned by half-warp lane hl: two granules per plane
+__device__ __forceinline__ void store_oprow16(unsigned char* img, int nck, long long Q, long long q, int hl, int K, const float4 (&v)[4]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int gk = 2 * hl + h;
+    if (8 * gk >= K) continue;
+    const float f[8] = {v[2 * h].x, v[2 * h].y, v[2 * h].z, v[2 * h].w, v[2 * h + 1].x, v[2 * h + 1].y, v[2 * h + 1].z, v[2 * h + 1].w};
+    uint4 hi, lo;
+    tc::split8(f, hi, lo);
+    *reinterpret_cast<uint4*>(oprow_ptr(img, 0, nck, Q, q, gk)) = hi;
+    *reinterpret_cast<uint4*>(oprow_ptr(img, 1, nck, Q, q, gk)) = lo;
+  }
 }
 
-// x_v -> operand row (layer 0)
-__device__ __forceinline__ void convert_x_row(const ClusterP& P, const CDir& D, int d, int p, long long q, int lane) {
-  if (8 * lane >= P.Kx) return;
-  const float* src = P.X + (size_t)D.perm[p] * P.ldx;
-  float v[8];
-  const int k0 = 8 * lane;
-  if (P.vec_x) {
-    Row8 R;
-    load_row8(R, src, k0, (P.Din + 3) & ~3);
+// x_v -> operand rows (layer 0): rows r = first, first + stride, ... of a level, two of them in flight per half-warp
+__device__ __forceinline__ void convert_x_rows(const ClusterP& P, const CDir& D, int d, int pos0, int q0, int n, int first, int stride,
+                                               int hl) {
+  const int k0 = 16 * hl;
+  if (k0 >= P.Kx) return;
+  const int w4 = (P.Din + 3) & ~3;
+  for (int r = first; r < n; r += 2 * stride) {
+    Row16 R[2];
+    bool on[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = R.v[j];
-  } else {
+    for (int t = 0; t < 2; ++t) {
+      const int rr = r + t * stride;
+      on[t] = rr < n;
+      const float* src = P.X + (size_t)(on[t] ? D.perm[pos0 + rr] : 0) * P.ldx;
+      if (P.vec_x) {
+        load_row16(R[t], src, k0, w4, on[t]);
+      } else {
+        float f[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < P.Din) ? __ldcg(src + k0 + j) : 0.f;
+        for (int j = 0; j < 16; ++j) f[j] = (on[t] && k0 + j < P.Din) ? __ldcg(src + k0 + j) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) R[t].v[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (on[t]) store_oprow16(P.ximg[d], P.nckx, P.Q, (long long)q0 + r + t * stride, hl, P.Kx, R[t].v);
   }
-  store_oprow(P.ximg[d], P.nckx, P.Q, q, lane, v);
 }
 
 // score of one in-edge apart from the key term: edge type + vertex id (constants per destination cancel)
@@ -175,135 +220,79 @@ __device__ __forceinline__ float edge_terms(const ClusterP& P, const CDir& D, co
   return sc;
 }
 
-// m_v = sum_e softmax_e(score_e) h_e over ALL in-edges of position p; a predecessor that is not in an earlier level
-// (col >= first position of this level) scores without its key term, keeps its softmax mass and adds a zero row (Q1)
-__device__ __forceinline__ void gather_row(const ClusterP& P, const CDir& D, const CLay& Lp, int p, long long q, int lstart, int lane,
-                                           const float (&wk)[8]) {
-  const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
-  const int ne = e1 - e0;
-  const int k0 = 8 * lane;
-  const int w4 = P.Hq;
+// In-edges e = e_first + (t << ls), t = 0, 1, ..., below e_end, folded into the running softmax state A of this half-warp's
+// node. A predecessor that is not in an earlier level (col >= first position of this level) scores without its key term,
+// keeps its softmax mass and adds a zero row. Both half-warps of a warp run the same number of rounds.
+__device__ __forceinline__ void gather_edges(const ClusterP& P, const CDir& D, const CLay& Lp, int e_first, int e_end, int ls, int lstart,
+                                             int hl, const float4 (&wk)[4], float ca0, float ca1, GAcc& A) {
+  const int k0 = 16 * hl, w4 = P.Hq;
   const float* __restrict__ Hs = Lp.Hs;
-  const float ca0 = D.eattr ? __ldg(Lp.attnc) : 0.f, ca1 = D.eattr ? __ldg(Lp.attnc + 1) : 0.f;
-  float m[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = 0.f;
-  if (ne > 0 && ne <= 4) {
-    // ---- the common case: every predecessor row stays in registers between the score and the weighted sum
-    Row8 R[4];
-    float sc[4];
+  int nb = e_end > e_first ? (((e_end - e_first - 1) >> ls) >> 2) + 1 : 0;
+  nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, 16));
+#pragma unroll 1
+  for (int b = 0; b < nb; ++b) {
+    Row16 R[4];
+    float sc[4], dt[4];
     bool val[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      sc[t] = -INFINITY; val[t] = false;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
-      if (t < ne) {
-        const int sp = D.col[e0 + t];
-        val[t] = sp < lstart;
-        if (val[t]) load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
-        sc[t] = edge_terms(P, D, Lp, e0 + t, sp, ca0, ca1);
-      }
+      const int e = e_first + ((4 * b + t) << ls);
+      const bool live = e < e_end;
+      const int sp = live ? D.col[e] : 0;
+      val[t] = live && sp < lstart;
+      load_row16(R[t], Hs + (size_t)sp * P.ldh, k0, w4, val[t]);
+      sc[t] = live ? edge_terms(P, D, Lp, e, sp, ca0, ca1) : -INFINITY;
     }
-    float dt[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
+    for (int t = 0; t < 4; ++t) dt[t] = dot16(R[t], wk);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
     }
-    float mx = -INFINITY;
+    float bm = -INFINITY;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      if (t < ne) { if (val[t]) sc[t] += dt[t]; mx = fmaxf(mx, sc[t]); }
+      if (val[t]) sc[t] += dt[t];
+      bm = nanmax(bm, sc[t]);
     }
-    float den = 0.f, ex[4];
+    if (bm == -INFINITY) continue;                       // nothing of this node in this round (the other half-warp is still going)
+    const float mnew = nanmax(A.mx, bm);
+    const float scale = expf(A.mx - mnew);               // 0 on the first round (running max = -inf)
+    float s = 0.f, w[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { ex[t] = (t < ne) ? expf(sc[t] - mx) : 0.f; den += ex[t]; }
-    const float inv = 1.f / (den + 1e-16f);
+    for (int t = 0; t < 4; ++t) { w[t] = expf(sc[t] - mnew); s += w[t]; }       // dead edges: exp(-inf) = 0
+    A.den = fmaf(A.den, scale, s);
+    A.mx = mnew;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float a = val[t] ? ex[t] * inv : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaf(a, R[t].v[j], m[j]);
-    }
-  } else if (ne > 4) {
-    // ---- long in-edge lists: softmax statistics first (online), then the weighted rows; four rows in flight
-    float mx = -INFINITY, den = 0.f;
-    for (int eb = e0; eb < e1; eb += 4) {
-      Row8 R[4];
-      float sc[4], dt[4];
-      bool val[4];
+    for (int j = 0; j < 4; ++j) {
+      float4 m = A.m[j];
+      m.x *= scale; m.y *= scale; m.z *= scale; m.w *= scale;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        sc[t] = -INFINITY; val[t] = false;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
-        if (eb + t < e1) {
-          const int sp = D.col[eb + t];
-          val[t] = sp < lstart;
-          if (val[t]) load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
-          sc[t] = edge_terms(P, D, Lp, eb + t, sp, ca0, ca1);
-        }
+        const float a = val[t] ? w[t] : 0.f;
+        m.x = fmaf(a, R[t].v[j].x, m.x); m.y = fmaf(a, R[t].v[j].y, m.y); m.z = fmaf(a, R[t].v[j].z, m.z); m.w = fmaf(a, R[t].v[j].w, m.w);
       }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
-      }
-      float bm = -INFINITY;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (eb + t < e1) { if (val[t]) sc[t] += dt[t]; bm = fmaxf(bm, sc[t]); }
-      }
-      const float mnew = fmaxf(mx, bm);
-      float s = 0.f;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) s += (eb + t < e1) ? expf(sc[t] - mnew) : 0.f;
-      den = den * expf(mx - mnew) + s;
-      mx = mnew;
-    }
-    const float inv = 1.f / (den + 1e-16f);
-    for (int eb = e0; eb < e1; eb += 4) {
-      Row8 R[4];
-      float sc[4], dt[4];
-      bool val[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        sc[t] = 0.f; val[t] = false;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) R[t].v[j] = 0.f;
-        if (eb + t < e1) {
-          const int sp = D.col[eb + t];
-          val[t] = sp < lstart;
-          if (val[t]) {
-            load_row8(R[t], Hs + (size_t)sp * P.ldh, k0, w4);
-            sc[t] = edge_terms(P, D, Lp, eb + t, sp, ca0, ca1);
-          }
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) dt[t] = dot8(R[t], wk);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) dt[t] += __shfl_xor_sync(0xffffffffu, dt[t], o);
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float a = val[t] ? expf(sc[t] + dt[t] - mx) * inv : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaf(a, R[t].v[j], m[j]);
-      }
+      A.m[j] = m;
     }
   }
-  if (k0 < P.Kh) store_oprow(Lp.mimg, P.nckh, P.Q, q, lane, m);
+}
+__device__ __forceinline__ void gacc_init(GAcc& A) {
+  A.mx = -INFINITY; A.den = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) A.m[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// m_v = (weighted sum) / (denominator + 1e-16) (PyG softmax), stored as an operand row and in fp32
+__device__ __forceinline__ void finish_row(const ClusterP& P, const CLay& Lp, int p, long long q, int hl, GAcc& A) {
+  const float inv = 1.f / (A.den + 1e-16f);
+  const int k0 = 16 * hl;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { A.m[j].x *= inv; A.m[j].y *= inv; A.m[j].z *= inv; A.m[j].w *= inv; }
+  store_oprow16(Lp.mimg, P.nckh, P.Q, q, hl, P.Kh, A.m);
   float* mo = Lp.m32 + (size_t)p * P.ldh + k0;
-  if (k0 + 4 <= w4) *reinterpret_cast<float4*>(mo) = make_float4(m[0], m[1], m[2], m[3]);
-  if (k0 + 8 <= w4) *reinterpret_cast<float4*>(mo + 4) = make_float4(m[4], m[5], m[6], m[7]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (k0 + 4 * j + 4 <= P.Hq) *reinterpret_cast<float4*>(mo + 4 * j) = A.m[j];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -318,12 +307,19 @@ __device__ __forceinline__ int lower_bound_dev(const int* a, int n, int key) {  
   return lo;
 }
 
+// issuer-side state of the operand slots. The 96 KB operand region is cut per projection chunk into as many stages (hi tile
+// + lo tile of the chunk's rows, rounded up to 32) as fit: chunks of <= 32 rows get 12 stages — every k chunk of both
+// operands lands in its own stage, all bulk copies of the chunk are in flight at once — full 128-row chunks cycle through 3.
+struct Slots {
+  uint32_t full_par, empty_par;      // bit s: parity of the next wait on full[s]; parity of the next commit on empty[s]
+};
+
 __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_constant__ ClusterP P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* Wih = base;                                    // [plane][k chunk][96 rows x 128 B]
   unsigned char* Ring = base + kWBytes;
-  CSmemTail& S = *reinterpret_cast<CSmemTail*>(Ring + (size_t)kCNStage * kCStageBytes);
+  CSmemTail& S = *reinterpret_cast<CSmemTail*>(Ring + (size_t)kCRingBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
   const int item = (int)cluster_idx();
@@ -338,9 +334,10 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   unsigned char* inimg = first_layer ? P.ximg[d] : P.lay[d][i - 1].himg;
 
   if (tid == 0) {
-    for (int s = 0; s < kCNStage; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < kCSlots; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     mbar_init(&S.acc_full, 1);
     mbar_init(&S.tmem_free, kCWorkWarps);
+    S.nlong = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tc::tmem_alloc(&S.tmem_slot, 512);
@@ -420,9 +417,12 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
       S.bias[b][uu] = (uu < P.U && u < P.HP) ? __ldg(Lp.bias + (size_t)b * P.HP + u) : 0.f;
     }
   }
-  float wk[8];                                                  // key weights of the lane's k slice (gather phase)
+  const int hl = lane & 15;
+  float4 wk[4];                                                 // key weights of the half-warp lane's k slice (gather phase)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wk[j] = (8 * lane + j < P.HP) ? __ldg(Lp.wk + 8 * lane + j) : 0.f;
+  for (int j = 0; j < 4; ++j)
+    wk[j] = (16 * hl + 4 * j + 4 <= P.HP) ? __ldg(reinterpret_cast<const float4*>(Lp.wk + 16 * hl + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float ca0 = D.eattr ? __ldg(Lp.attnc) : 0.f, ca1 = D.eattr ? __ldg(Lp.attnc + 1) : 0.f;
   tc::fence_async_smem();                // W_ih tiles were written with ordinary stores, the tensor core reads them
   tc::fence_before_sync();
   __syncthreads();
@@ -430,171 +430,282 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   cluster_sync_all();
 
   const uint32_t wih_s = smem_u32(Wih), ring_s = smem_u32(Ring);
-  uint32_t jring = 0, ct = 0;            // ring stages used so far, chunks done so far
-  const int gw = warp * kCS + rank;      // worker warp index in the cluster (rank-minor: a short level spreads over the CTAs)
+  uint32_t ct = 0;                       // projection chunks done so far
+  Slots SL = {0u, 0u};
+  // half-warp index in the cluster, rank-minor: a short level spreads over the CTAs
+  const int ghw = ((lane >> 4) * kCWorkWarps + warp) * kCS + rank;
+  constexpr int kHalfWarps = kCS * kCWorkWarps * 2;            // 128
+
+  // layer 0: the operand rows of level 0's inputs (those of level l + 1 are converted during level l)
+  if (first_layer && L > 0) {
+    const int4 T0 = __ldcg(tab);
+    if (warp < kCWorkWarps) convert_x_rows(P, D, d, T0.x, T0.z, T0.y, ghw, kHalfWarps, hl);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    cluster_sync_all();
+  }
 
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const int4 T = __ldcg(tab + l);
+    const int4 Tn = (first_layer && l + 1 < L) ? __ldcg(tab + l + 1) : make_int4(0, 0, 0, 0);
     const int pos0 = T.x, n = T.y, q0 = T.z, lstart = T.w;
     long long* tr = (P.trace && l < P.max_levels) ? P.trace + (((size_t)l * 256 + blockIdx.x) << 4) : nullptr;
     if (tr && tid == 0) tr[0] = clock64();
-    if (n > 0) {
-      // ---------------- gather phase ----------------
-      const bool exchange = l > 0 || first_layer;
-      if (warp < kCWorkWarps) {
-        for (int r = gw; r < n; r += kCS * kCWorkWarps) {
-          if (first_layer) convert_x_row(P, D, d, pos0 + r, (long long)q0 + r, lane);
-          if (l > 0) gather_row(P, D, Lp, pos0 + r, (long long)q0 + r, lstart, lane, wk);
+    if (n == 0) break;                     // a group without nodes at this level has none at deeper ones
+    const int nchunks = (n + kRC - 1) / kRC;
+    const bool exchange = l > 0;           // the aggregates of this level travel through global memory to every CTA
+
+    // one projection chunk from the issuer's side. part 1 = bulk copies of every stage that has its own slot + the MMAs of
+    // the input operand; part 2 (after the exchange barrier for chunk 0) = the aggregate operand
+    auto issue_chunk = [&](int c, int part_lo, int part_hi) {
+      const int r0 = c * kRC;
+      const int rows = min(kRC, n - r0);
+      const int rp = (rows + 31) & ~31;                        // rows of a stage tile
+      const uint32_t stage_bytes = 2u * (uint32_t)rp * tc::ROW_BYTES;
+      const int nslots = rp <= 32 ? 12 : rp <= 64 ? 6 : rp <= 96 ? 4 : 3;
+      const uint32_t bytes = (uint32_t)((rows + 7) & ~7) * tc::ROW_BYTES;
+      const int ns = nck_in + (l > 0 ? P.nckh : 0);
+      const uint32_t idesc = uni(tc::instr_desc_f16(128, (rows + 15) & ~15));
+      auto load_stage = [&](int k) {
+        const int slot = k % nslots;
+        if (k >= nslots) {                                     // the MMAs of stage k - nslots read this slot: committed, wait
+          mbar_wait(&S.empty[slot], ((SL.empty_par >> slot) & 1u) ^ 1u);
         }
+        if (elect_one()) {
+          const bool is_in = k < nck_in;
+          const int kc = is_in ? k : k - nck_in;
+          unsigned char* img = is_in ? inimg : Lp.mimg;
+          const int nck = is_in ? nck_in : P.nckh;
+          const unsigned char* src_hi = img + ((((size_t)0 * nck + kc) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
+          const unsigned char* src_lo = img + ((((size_t)1 * nck + kc) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
+          unsigned char* dst = Ring + (size_t)slot * stage_bytes;
+          mbar_expect_tx(&S.full[slot], 2 * bytes);
+          bulk_g2s(dst, src_hi, bytes, &S.full[slot]);
+          bulk_g2s(dst + (size_t)rp * tc::ROW_BYTES, src_lo, bytes, &S.full[slot]);
+        }
+        __syncwarp();
+      };
+      if (part_lo == 0 && !first_layer) {
+        // the input rows of this chunk are the states the cluster of the layer below has published: every one of its CTAs
+        // counts the chunks whose unit slice it has stored (same level tables on both sides, so chunk numbers agree)
+        const unsigned int* fl = P.flags + (size_t)(item - P.dirs * P.G) * kCS + (lane & (kCS - 1));
+        while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= ct + 1u)) {}
+        asm volatile("fence.proxy.async;" ::: "memory");
       }
-      if (tr && tid == 0) tr[1] = clock64();
-      if (exchange) {
-        asm volatile("fence.proxy.async;" ::: "memory");        // operand rows: ordinary stores here, bulk copies (async proxy) there
-        cluster_sync_all();
+      if (part_lo == 0) {
+        // the previous chunk's MMAs are done (its accumulators were complete before its epilogue began, and this chunk is only
+        // issued behind that epilogue's end or the level barrier): every slot is free, the region may be re-cut
+        if (ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);
+        tc::fence_after_sync();
       }
-      if (tr && tid == 0) tr[2] = clock64();
-      // ---------------- projection + cell ----------------
+      const int k_lo = part_lo == 0 ? 0 : nck_in, k_hi = part_hi == 2 ? ns : nck_in;
+      // a stage may be copied once the stage that used its slot before (k - nslots) has had its MMAs issued: at the start of
+      // a part that holds for every k < k_lo + nslots — with 12 slots the whole chunk is in flight at once
+      int loaded = k_lo;
+      while (loaded < k_hi && loaded < k_lo + nslots) load_stage(loaded++);
 #pragma unroll 1
-      for (int r0 = 0; r0 < n; r0 += kRC) {
-        const int rows = min(kRC, n - r0);
-        const uint32_t bytes = (uint32_t)((rows + 7) & ~7) * tc::ROW_BYTES;
-        const int ns = nck_in + (l > 0 ? P.nckh : 0);           // stages of this chunk: input operand chunks, then aggregate chunks
-        if (warp == kCWorkWarps) {
-          // ---- issuer warp (converged; one elected lane issues)
-          if (!first_layer && r0 == 0) {
-            const unsigned int* fl = P.flags + (item - P.dirs * P.G);       // cluster (i - 1, d, g)
-            while (ld_acquire_u32(fl) < (unsigned int)(l + 1)) {}
-            asm volatile("fence.proxy.async;" ::: "memory");
-          }
-          const uint32_t idesc = uni(tc::instr_desc_f16(128, (rows + 15) & ~15));
-          auto load_stage = [&](int k) {
-            const uint32_t j = jring + (uint32_t)k, st = j % kCNStage, use = j / kCNStage;
-            if (use >= 1) mbar_wait(&S.empty[st], (use - 1) & 1u);
-            if (elect_one()) {
-              const bool is_in = k < nck_in;
-              const int c = is_in ? k : k - nck_in;
-              unsigned char* img = is_in ? inimg : Lp.mimg;
-              const int nck = is_in ? nck_in : P.nckh;
-              const unsigned char* src_hi = img + ((((size_t)0 * nck + c) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
-              const unsigned char* src_lo = img + ((((size_t)1 * nck + c) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
-              unsigned char* dst = Ring + (size_t)st * kCStageBytes;
-              mbar_expect_tx(&S.full[st], 2 * bytes);
-              bulk_g2s(dst, src_hi, bytes, &S.full[st]);
-              bulk_g2s(dst + kRC * tc::ROW_BYTES, src_lo, bytes, &S.full[st]);
+      for (int k = k_lo; k < k_hi; ++k) {
+        const int slot = k % nslots;
+        mbar_wait(&S.full[slot], (SL.full_par >> slot) & 1u);
+        SL.full_par ^= 1u << slot;
+        tc::fence_after_sync();
+        const bool is_in = k < nck_in;
+        const int kc = is_in ? k : k - nck_in;
+        const int Kop = is_in ? Kin : P.Kh;
+        const int nks = min(4, (Kop - 64 * kc) >> 4);
+        const uint32_t sb = uni(ring_s + (uint32_t)slot * stage_bytes);
+        const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)rp * tc::ROW_BYTES);
+        if (is_in) {
+          const uint32_t a0 = uni(wih_s + (uint32_t)kc * kWChunkBytes), a1 = uni(wih_s + (uint32_t)(nck_in + kc) * kWChunkBytes);
+          const uint64_t ah = tc::smem_desc(a0), al = tc::smem_desc(a1);
+          const uint32_t acc = uni(tmem + (uint32_t)kColAccX);
+          if (elect_one()) {
+            for (int ks = 0; ks < nks; ++ks) {
+              tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
+              tc::mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1u);
             }
-            __syncwarp();
-          };
-          for (int k = 0; k < min(2, ns); ++k) load_stage(k);
-#pragma unroll 1
-          for (int k = 0; k < ns; ++k) {
-            const uint32_t j = jring + (uint32_t)k, st = j % kCNStage, use = j / kCNStage;
-            mbar_wait(&S.full[st], use & 1u);
-            if (k == 0 && ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);   // the previous chunk's accumulators have been read
-            tc::fence_after_sync();
-            const bool is_in = k < nck_in;
-            const int c = is_in ? k : k - nck_in;
-            const int Kop = is_in ? Kin : P.Kh;
-            const int nks = min(4, (Kop - 64 * c) >> 4);
-            const uint32_t sb = uni(ring_s + st * (uint32_t)kCStageBytes);
-            const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)(kRC * tc::ROW_BYTES));
-            if (is_in) {
-              const uint32_t a0 = uni(wih_s + (uint32_t)c * kWChunkBytes), a1 = uni(wih_s + (uint32_t)(nck_in + c) * kWChunkBytes);
-              const uint64_t ah = tc::smem_desc(a0), al = tc::smem_desc(a1);
-              const uint32_t acc = uni(tmem + (uint32_t)kColAccX);
-              if (elect_one()) {
-                for (int ks = 0; ks < nks; ++ks) {
-                  tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (c == 0 && ks == 0) ? 0u : 1u);
-                  tc::mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
-                  tc::mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1u);
-                }
-              }
-            } else {
-              const uint32_t acc = uni(tmem + (uint32_t)kColAccH);
-              const uint32_t ah = uni(tmem + (uint32_t)(kColWhi + 32 * c)), al = uni(tmem + (uint32_t)(kColWlo + 32 * c));
-              if (elect_one()) {
-                for (int ks = 0; ks < nks; ++ks) {
-                  tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, (c == 0 && ks == 0) ? 0u : 1u);
-                  tc::mma_f16_ts(acc, ah + 8 * ks, bl + 2 * ks, idesc, 1u);
-                  tc::mma_f16_ts(acc, al + 8 * ks, bh + 2 * ks, idesc, 1u);
-                }
-              }
-            }
-            if (elect_one()) tc::commit(&S.empty[st]);
-            __syncwarp();
-            if (k + 2 < ns) load_stage(k + 2);
           }
-          if (elect_one()) tc::commit(&S.acc_full);
-          __syncwarp();
         } else {
-          // ---- worker warps: epilogue. TMEM lane = gate * 32 + unit, column = row of the chunk.
-          mbar_wait(&S.acc_full, ct & 1u);
-          tc::fence_after_sync();
-          const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
-          const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
-          const int u = u0 + 4 * ug;
-#pragma unroll 1
-          for (int s0 = 0; s0 < rows; s0 += kSub) {
-            if (qd < 3) {
-              float v[32];
-              if (acc_id == 0 || l > 0) {
-                tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)((acc_id ? kColAccH : kColAccX) + s0), v);
-                tc::wait_ld();
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.f;         // level 0: hidden state 0, nothing was projected
-              }
-              float* dst = &S.stage[acc_id][32 * qd + lane][0];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j] = v[j];
+          const uint32_t acc = uni(tmem + (uint32_t)kColAccH);
+          const uint32_t ah = uni(tmem + (uint32_t)(kColWhi + 32 * kc)), al = uni(tmem + (uint32_t)(kColWlo + 32 * kc));
+          if (elect_one()) {
+            for (int ks = 0; ks < nks; ++ks) {
+              tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_f16_ts(acc, ah + 8 * ks, bl + 2 * ks, idesc, 1u);
+              tc::mma_f16_ts(acc, al + 8 * ks, bh + 2 * ks, idesc, 1u);
             }
-            workers_sync();
-            const int rr = s0 + row;
-            if (rr < rows && 4 * ug < P.U) {
-              const int p = pos0 + r0 + rr;
-              float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
-              const bool in_row = u + 4 <= P.Hq;
-              if (l > 0 && in_row) mv = ldcg4(Lp.m32 + (size_t)p * P.ldh + u);
-              float o[4];
-              const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int uu = 4 * ug + k;
-                const float xr = S.stage[0][uu][row], xz = S.stage[0][32 + uu][row], xn = S.stage[0][64 + uu][row];
-                const float hr = S.stage[1][uu][row], hz = S.stage[1][32 + uu][row], hn = S.stage[1][64 + uu][row];
-                const float rg = fast_sigmoid(xr + hr + S.bias[0][uu]);
-                const float zg = fast_sigmoid(xz + hz + S.bias[1][uu]);
-                const float ng = fast_tanh(xn + S.bias[2][uu] + rg * (hn + S.bias[3][uu]));
-                o[k] = ng + zg * (mm[k] - ng);
-              }
-              if (in_row) *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
-              if (has_next && u < P.Kh) {
-                uint32_t h0, h1, l0, l1;
-                tc::split2(o[0], o[1], h0, l0);
-                tc::split2(o[2], o[3], h1, l1);
-                const long long q = (long long)q0 + r0 + rr;
-                unsigned char* ph = oprow_ptr(Lp.himg, 0, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
-                unsigned char* pl = oprow_ptr(Lp.himg, 1, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
-                *reinterpret_cast<uint2*>(ph) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
-              }
-            }
-            workers_sync();
           }
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&S.tmem_free);
         }
-        jring += (uint32_t)ns;
-        ct += 1;
+        if (elect_one()) tc::commit(&S.empty[slot]);
+        __syncwarp();
+        SL.empty_par ^= 1u << slot;
+        // keep the slots busy: the next stage goes where stage k was once its MMAs are done
+        if (loaded < k_hi && loaded - nslots <= k) load_stage(loaded++);
       }
-      if (tr && tid == 0) tr[3] = clock64();
-      // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
-      asm volatile("fence.proxy.async;" ::: "memory");
-      cluster_sync_all();
-      if (tr && tid == 0) tr[4] = clock64();
+      if (part_hi == 2) {
+        if (elect_one()) tc::commit(&S.acc_full);
+        __syncwarp();
+      }
+    };
+
+    // ---------------- gather phase (workers) / input part of the first chunk (issuer) ----------------
+    if (warp < kCWorkWarps) {
+      // short levels: the dependent-load chains of the two jobs would add up in a warp, so warps 0..3 gather and warps 4..7
+      // convert the next level's input rows at the same time
+      const bool split = first_layer && exchange && n <= kHalfWarps / 2 && Tn.y <= kHalfWarps / 2;
+      const int ghw_s = (((lane >> 4) * (kCWorkWarps / 2) + (warp & 3)) * kCS + rank);      // half-warp index among 64
+      if (split && warp >= kCWorkWarps / 2) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw_s, kHalfWarps / 2, hl);
+      if (exchange) {
+        const int first = split ? (warp < kCWorkWarps / 2 ? ghw_s : n) : ghw;
+        const int stride = split ? kHalfWarps / 2 : kHalfWarps;
+        for (int r = first; __any_sync(0xffffffffu, r < n); r += stride) {
+          const bool on = r < n;
+          const int p = pos0 + (on ? r : 0);
+          int e0 = 0, e1 = 0;
+          if (on) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
+          bool lng = e1 - e0 > kLongEdges;                     // split over the CTA's half-warps below, if the list has room
+          int slot = 0;
+          if (lng && hl == 0) slot = atomicAdd(&S.nlong, 1);
+          slot = __shfl_sync(0xffffffffu, slot, lane & 16);
+          if (lng) {
+            if (slot < kMaxLong) { if (hl == 0) S.longrow[slot] = r; e1 = e0; } else lng = false;
+          }
+          GAcc A;
+          gacc_init(A);
+          gather_edges(P, D, Lp, e0, e1, 0, lstart, hl, wk, ca0, ca1, A);
+          if (on && !lng) finish_row(P, Lp, p, (long long)q0 + r, hl, A);
+        }
+        workers_sync();
+        const int nl = min(S.nlong, kMaxLong);
+        float* part = &S.stage[0][0][0];                       // [16 half-warps][kPartLd]
+        for (int j = 0; j < nl; ++j) {
+          const int r = S.longrow[j];
+          const int p = pos0 + r;
+          const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
+          const int hw = 2 * warp + (lane >> 4);
+          GAcc A;
+          gacc_init(A);
+          gather_edges(P, D, Lp, e0 + hw, e1, 4, lstart, hl, wk, ca0, ca1, A);
+          float* mine = part + hw * kPartLd;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(mine + 16 * hl + 4 * q) = A.m[q];
+          if (hl == 0) { mine[256] = A.mx; mine[257] = A.den; }
+          workers_sync();
+          {                                                    // thread = k: merge the 16 partial softmax states
+            float M = -INFINITY;
+#pragma unroll
+            for (int h = 0; h < 16; ++h) M = nanmax(M, part[h * kPartLd + 256]);
+            float den = 0.f, acc = 0.f;
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+              const float w = expf(part[h * kPartLd + 256] - M);
+              den = fmaf(part[h * kPartLd + 257], w, den);
+              acc = fmaf(part[h * kPartLd + tid], w, acc);
+            }
+            const float v = acc / (den + 1e-16f);
+            if (tid < P.Hq) Lp.m32[(size_t)p * P.ldh + tid] = v;
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __shfl_sync(0xffffffffu, v, (lane & ~7) + q);
+            if ((lane & 7) == 0 && tid < P.Kh) {
+              uint4 hi, lo;
+              tc::split8(f, hi, lo);
+              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 0, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = hi;
+              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 1, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = lo;
+            }
+          }
+          workers_sync();
+        }
+        if (tid == 0) S.nlong = 0;
+      }
+      if (first_layer && !split && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
+    } else {
+      issue_chunk(0, 0, exchange ? 1 : 2);
     }
-    if (has_next && rank == 0 && tid == 0) st_release_u32(P.flags + item, (unsigned int)(l + 1));
+    if (tr && tid == 0) tr[1] = clock64();
+    if (exchange) {
+      asm volatile("fence.proxy.async;" ::: "memory");          // operand rows: ordinary stores here, bulk copies (async proxy) there
+      cluster_sync_all();
+    }
+    if (tr && tid == 0) tr[2] = clock64();
+    // ---------------- projection + cell ----------------
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int r0 = c * kRC;
+      const int rows = min(kRC, n - r0);
+      if (warp == kCWorkWarps) {
+        if (c == 0) { if (exchange) issue_chunk(0, 1, 2); }
+        else issue_chunk(c, 0, 2);
+      } else {
+        // ---- worker warps: epilogue. TMEM lane = gate * 32 + unit, column = row of the chunk.
+        mbar_wait(&S.acc_full, ct & 1u);
+        tc::fence_after_sync();
+        const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
+        const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
+        const int u = u0 + 4 * ug;
+#pragma unroll 1
+        for (int s0 = 0; s0 < rows; s0 += kSub) {
+          if (qd < 3) {
+            float v[32];
+            if (acc_id == 0 || l > 0) {
+              tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)((acc_id ? kColAccH : kColAccX) + s0), v);
+              tc::wait_ld();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;         // level 0: hidden state 0, nothing was projected
+            }
+            float* dst = &S.stage[acc_id][32 * qd + lane][0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = v[j];
+          }
+          workers_sync();
+          const int rr = s0 + row;
+          if (rr < rows && 4 * ug < P.U) {
+            const int p = pos0 + r0 + rr;
+            float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool in_row = u + 4 <= P.Hq;
+            if (l > 0 && in_row) mv = ldcg4(Lp.m32 + (size_t)p * P.ldh + u);
+            float o[4];
+            const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int uu = 4 * ug + k;
+              const float xr = S.stage[0][uu][row], xz = S.stage[0][32 + uu][row], xn = S.stage[0][64 + uu][row];
+              const float hr = S.stage[1][uu][row], hz = S.stage[1][32 + uu][row], hn = S.stage[1][64 + uu][row];
+              const float rg = fast_sigmoid(xr + hr + S.bias[0][uu]);
+              const float zg = fast_sigmoid(xz + hz + S.bias[1][uu]);
+              const float ng = fast_tanh(xn + S.bias[2][uu] + rg * (hn + S.bias[3][uu]));
+              o[k] = ng + zg * (mm[k] - ng);
+            }
+            if (in_row) *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
+            if (has_next && u < P.Kh) {
+              uint32_t h0, h1, l0, l1;
+              tc::split2(o[0], o[1], h0, l0);
+              tc::split2(o[2], o[3], h1, l1);
+              const long long q = (long long)q0 + r0 + rr;
+              unsigned char* ph = oprow_ptr(Lp.himg, 0, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+              unsigned char* pl = oprow_ptr(Lp.himg, 1, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+              *reinterpret_cast<uint2*>(ph) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
+            }
+          }
+          if (has_next && s0 + kSub >= rows) asm volatile("fence.proxy.async;" ::: "memory");   // the next layer bulk-copies these rows
+          workers_sync();
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.tmem_free);
+        // behind the last pass's closing workers_sync: the whole CTA has stored its slice of the chunk's states
+        if (has_next && tid == 0) st_release_u32(P.flags + (size_t)item * kCS + rank, ct + 1u);
+      }
+      ct += 1;
+    }
+    if (tr && tid == 0) tr[3] = clock64();
+    // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
+    asm volatile("fence.proxy.async;" ::: "memory");
+    cluster_sync_all();
+    if (tr && tid == 0) tr[4] = clock64();
   }
   tc::fence_before_sync();
   __syncthreads();

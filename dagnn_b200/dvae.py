@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import runtime as rt
 from .data import DagBatch, collate_dvae
-from .ogb import AttnConv, NA_ATTN_H, P_MAX, _forward_only_guard
+from .ogb import AttnConv, NA_ATTN_H, P_MAX, _PackedCacheMixin, _forward_only_guard
 
 
 class _DVAEParams(nn.Module):
@@ -73,7 +73,7 @@ class _DVAEParams(nn.Module):
         raise NotImplementedError("sampling decode (dvae/models_pyg.py:338-396) is SURVEY.md §8f row 2")
 
 
-class _DagnnDvaeBase(_DVAEParams):
+class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
     _VID = True   # NA: one-hot vertex ids on keys (dvae/dagnn.py:130-139); BN: none
 
     def _init_dagnn(self, emb_dim, hidden_dim, out_dim, num_layers, bidirectional, agg, out_wx, out_pool_all, out_pool,
@@ -85,6 +85,9 @@ class _DagnnDvaeBase(_DVAEParams):
                                       "(scripts/na_train.sh, bn_train.sh use neither)")
         if hidden_dim != self.hs:
             raise ValueError("hidden_dim must equal hs (the GRU cells are grue_forward/backward, dagnn.py:73-75)")
+        if emb_dim != self.nvt:
+            raise ValueError("emb_dim must equal nvt: the first GRU cell is GRUCell(nvt, hs) and reads G.x (dvae/models_pyg.py:37, "
+                             "dvae/dagnn.py:140-144)")
         self.num_nodes = num_nodes
         self.agg, self.agg_attn, self.agg_attn_x = agg, True, False
         self.bidirectional = bidirectional

@@ -53,13 +53,26 @@ class AttnConv(nn.Module):
         self.attn_lin = nn.Linear(attn_q_dim + attn_dim, 1)
 
 
+class _PackedCacheMixin(object):
+    """Drops the packed-parameter cache whenever parameters may have been rewritten behind autograd's version counters."""
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._packed.invalidate()
+        return out
+
+    def train(self, mode: bool = True):
+        self._packed.invalidate()
+        return super().train(mode)
+
+
 def _forward_only_guard(module: nn.Module):
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
         raise RuntimeError("dagnn_b200 implements the forward pass only (backward is SURVEY.md §8f row 1): call the "
                            "module under torch.no_grad() / torch.inference_mode(). There is no autograd fallback.")
 
 
-class DAGNN(nn.Module):
+class DAGNN(_PackedCacheMixin, nn.Module):
 
     def __init__(self, num_vocab, max_seq_len, emb_dim, hidden_dim, out_dim,
                  num_rels=2, w_edge_attr=True, num_layers=2, bidirectional=True, mapper_bias=True,
@@ -165,7 +178,12 @@ class DAGNN(nn.Module):
         return rt.readout(sched, blocks, self.out_pool, col, X.device)
 
     def forward_readout(self, G):
-        """The north-star hot path: encoder -> schedule -> level sweeps (both directions) -> pooled readout."""
+        """The north-star hot path: encoder -> schedule -> level sweeps (both directions) -> pooled readout.
+        A batch without nodes (a rank that owns no graph) gives an empty [0, out_hidden_dim] readout, like the reference's
+        collater, which drops empty shards (tg/dataloader.py:29-31)."""
+        if G.x.shape[0] == 0:
+            return torch.zeros(0, self.out_hidden_dim, device=G.x.device, dtype=torch.float32)
+
         def run(max_levels):
             X, Hs, sched = self.node_states(G, None, max_levels)
             return self.readout(G, X, Hs, sched), sched

@@ -6,6 +6,7 @@ torch tensor and handed to libdagnn_sm100.so as a raw pointer. No arithmetic of 
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -96,6 +97,7 @@ def dag_levels(edge_index: torch.Tensor, num_nodes: int, max_passes: int = 257):
 
 
 _LAYOUTS = {}      # (N, E, B, dirs, max_levels, has edge attributes) -> (offsets, total, workspace bytes) of a schedule buffer
+_LOCK = threading.Lock()     # module-level caches (_LAYOUTS, _WS): forward may run in one host thread per GPU (tg/data_parallel.py:60-61)
 
 
 class Schedule(object):
@@ -134,7 +136,8 @@ class Schedule(object):
         ML = int(max_levels)
         head = 8 + dirs * (ML + 1)
         lkey = (N, E, B, dirs, ML, edge_attr is not None)
-        lay = _LAYOUTS.get(lkey)
+        with _LOCK:
+            lay = _LAYOUTS.get(lkey)
         if lay is None:
             sizes = [("head", head)]
             for d in range(dirs):
@@ -146,9 +149,11 @@ class Schedule(object):
             for k, n in sizes:
                 offs[k] = tot
                 tot += _align(max(n, 1))
-            if len(_LAYOUTS) > 64:
-                _LAYOUTS.clear()
-            lay = _LAYOUTS[lkey] = (offs, tot, int(lib().dagnn_schedule_workspace_bytes(N, E, ML)))
+            lay = (offs, tot, int(lib().dagnn_schedule_workspace_bytes(N, E, ML)))
+            with _LOCK:
+                if len(_LAYOUTS) > 64:
+                    _LAYOUTS.clear()
+                _LAYOUTS[lkey] = lay
         offs, tot, ws_bytes = lay
         buf = torch.empty(tot + (ws_bytes + 3) // 4, device=dev, dtype=torch.int32)
         s.buf, s.head_len, s.max_levels = buf, head, ML
@@ -288,12 +293,31 @@ def run_checked(fn, max_levels: int = 256):
 
 
 class PackedParams(object):
-    """Packed GRU + attention parameters of every (direction, layer); re-packed when a parameter changes."""
+    """Packed GRU + attention parameters of every (direction, layer); re-packed when a parameter changes.
+
+    The cache key is (storage pointer, tensor version) of every parameter: optimizer steps, `load_state_dict`, `.to()` and
+    in-place ops on the parameter bump it. Writes through `param.data` (e.g. `p.data.copy_()`, hand-rolled EMA) do NOT bump
+    the version — call `invalidate()` (the modules do it from `load_state_dict` / `train()` / `_apply`) after such edits."""
 
     def __init__(self):
         self.key = None
         self.blobs: List[List[torch.Tensor]] = []
         self.layouts: List[DagnnPackLayout] = []
+        self._lock = threading.Lock()
+
+    def invalidate(self):
+        with self._lock:
+            self.key = None
+
+    # a module carrying this cache stays deep-copyable / picklable (copy.deepcopy(model), torch.save(model)): the copy starts empty
+    def __deepcopy__(self, memo):
+        return PackedParams()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
 
     @staticmethod
     def layout(Din: int, H: int, nvid: int, first: bool, last: bool) -> DagnnPackLayout:
@@ -311,15 +335,26 @@ class PackedParams(object):
                 if use_edge_attr:
                     params.append(ag.edge_encoder.weight)
         key = tuple((p.data_ptr(), p._version) for p in params) + (Din, H, nvid, use_edge_attr, str(device))
-        if key == self.key:
-            return self
-        self.blobs, self.layouts = [], []
+        with self._lock:
+            if key == self.key:
+                return self
+            self._repack(cells, aggrs, Din, H, nvid, use_edge_attr, device)
+            self.key = key
+        return self
+
+    def _repack(self, cells, aggrs, Din: int, H: int, nvid: int, use_edge_attr: bool, device):
+        blobs, layouts = [], []
         for d in range(len(cells)):
             row = []
             for i in range(len(cells[d])):
                 cell, ag = cells[d][i], aggrs[d][i]
                 din = Din if i == 0 else H
                 nl = len(cells[d])
+                # the reference's GRUCell raises on a width mismatch; the pack kernel would read out of bounds instead
+                if tuple(cell.weight_ih.shape) != (3 * H, din) or tuple(cell.weight_hh.shape) != (3 * H, H) or \
+                        tuple(cell.bias_ih.shape) != (3 * H,) or tuple(cell.bias_hh.shape) != (3 * H,):
+                    raise _lib.DagnnError("GRU cell (%d, %d): weight_ih %s / weight_hh %s do not match input width %d, hidden %d"
+                                          % (d, i, tuple(cell.weight_ih.shape), tuple(cell.weight_hh.shape), din, H))
                 L = self.layout(din, H, nvid, i == 0, i + 1 == nl)
                 nxt = cells[d][i + 1].weight_ih.detach().contiguous() if i + 1 < nl else None
                 for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag.attn_lin.weight):
@@ -338,10 +373,9 @@ class PackedParams(object):
                       "dagnn_pack_params_f32")
                 row.append(blob)
                 if d == 0:
-                    self.layouts.append(L)
-            self.blobs.append(row)
-        self.key = key
-        return self
+                    layouts.append(L)
+            blobs.append(row)
+        self.blobs, self.layouts = blobs, layouts
 
 
 _WS = {}
@@ -349,11 +383,13 @@ _WS = {}
 
 def _sweep_workspace(device, dirs, layers, Din, H, N, E, max_levels) -> torch.Tensor:
     need = int(lib().dagnn_sweep_workspace_bytes(dirs, layers, Din, H, N, E, max_levels))
-    key = (device.type, device.index, _stream())
-    w = _WS.get(key)
+    key = (device.type, device.index, _stream(), threading.get_ident())     # never shared between concurrent forwards
+    with _LOCK:
+        w = _WS.get(key)
     if w is None or w.numel() * 4 < need:
         w = torch.zeros((need + 3) // 4, device=device, dtype=torch.int32)
-        _WS[key] = w
+        with _LOCK:
+            _WS[key] = w
     return w
 
 
@@ -363,6 +399,8 @@ def sweep(sched: Schedule, X: torch.Tensor, packed: PackedParams, Din: int, H: i
     (row p = node perm[d][p]). Asynchronous: level offsets / level count are read on the device."""
     X = _req_cuda(X, "X", torch.float32)
     dirs, N = sched.c.dirs, sched.c.N
+    if X.dim() != 2 or X.shape[0] != N or X.shape[1] != Din:
+        raise _lib.DagnnError("X must be [N=%d, Din=%d], got %s" % (N, Din, tuple(X.shape)))
     ldh = (H + 3) // 4 * 4
     Hs = torch.empty(dirs, num_layers, N, ldh, device=X.device, dtype=torch.float32)
     ws = _sweep_workspace(X.device, dirs, num_layers, Din, H, N, sched.c.E, sched.c.max_levels)
