@@ -1173,10 +1173,14 @@ extern "C" int dagnn_sweep_forward_f32(const DagnnSweepArgs* A, void* stream_) {
       DAGNN_REQUIRE(A->packed[d][i] && ((uintptr_t)A->packed[d][i] & 15) == 0, "sweep: packed params must be 16-byte aligned");
     }
   }
-  // DAGNN_SWEEP_PATH=grid forces the grid-wide kernel (A/B measurements, tests of both kernels); default: the cluster-resident
-  // sweep whenever the shape fits it
+  // Which kernel: the cluster-resident sweep wins while levels are short (its cost is the chain of levels: ~7 us per level and
+  // ~3.4 us per 64 rows of a level per cluster); the grid-wide sweep below spreads a big level over all 148 SMs and wins on
+  // large batches (measured: config 2, 66 k node-steps: 1.07 ms vs 1.66 ms; batch 4096, 2.1 M node-steps: 18.4 ms vs 16.4 ms).
+  // DAGNN_SWEEP_PATH=grid / cluster forces one of them (A/B measurements, tests of both kernels).
   const char* path_env = getenv("DAGNN_SWEEP_PATH");
-  if (!(path_env && strcmp(path_env, "grid") == 0)) {
+  const bool force_grid = path_env && strcmp(path_env, "grid") == 0, force_cluster = path_env && strcmp(path_env, "cluster") == 0;
+  const long long node_steps = (long long)S->N * dirs * layers;
+  if (!force_grid && (force_cluster || node_steps <= 600000)) {
     bool handled = false;
     if (int rc = cluster_forward(A, st, &handled)) return rc;
     if (handled) return DAGNN_OK;

@@ -34,20 +34,20 @@ namespace dagnn {
 
 constexpr int kCWorkWarps = 8;
 constexpr int kCWorkers = kCWorkWarps * 32;        // gather phase, epilogue
-constexpr int kCThreads = kCWorkers + 32;          // + the warp that issues bulk copies and MMAs
+constexpr int kCThreads = kCWorkers + 64;          // + one warp that issues the MMAs (warp 8) and one that issues the bulk copies (warp 9)
 constexpr int kCS = 8;                             // CTAs per cluster
 constexpr int kCMaxH = 256;                        // K of an operand row: 4 chunks of 64
 constexpr int kCU = kCMaxH / kCS;                  // hidden units per CTA at most (3 * 32 = 96 TMEM lanes)
-constexpr int kRC = 128;                           // rows per projection chunk (N of the MMAs)
-constexpr int kCStageBytes = 2 * kRC * tc::ROW_BYTES;      // hi + lo tile of 128 rows x 64 k = 32 KB
+constexpr int kRC = 64;                            // rows per projection chunk (N of the MMAs): two accumulator sets fit next to the weights
 constexpr int kCSlots = 12;                        // operand slots of 8 KB (hi + lo tile of 32 rows x 64 k)
-constexpr int kCRingBytes = 3 * kCStageBytes;      // 96 KB operand region
+constexpr int kCRingBytes = kCSlots * 8192;        // 96 KB operand region
 constexpr int kWRows = 96;                         // W_ih slice rows: gate * 32 + unit
 constexpr int kWChunkBytes = kWRows * tc::ROW_BYTES;       // 12 KB per (plane, k chunk)
 constexpr int kWBytes = 2 * 4 * kWChunkBytes;              // 96 KB
 constexpr int kSub = 32;                           // rows per epilogue pass
 constexpr int kSLd = 33;                           // stage row pitch (words): conflict-free both ways
-constexpr int kColWhi = 0, kColWlo = 128, kColAccX = 256, kColAccH = 384;   // TMEM column map (512 allocated)
+// TMEM column map (512 allocated): W_hh hi / lo tiles, then two accumulator sets {W_ih x (64 columns), W_hh m (64 columns)}
+constexpr int kColWhi = 0, kColWlo = 128, kColAcc = 256, kColSet = 128, kColAccH = 64;
 constexpr int kCMaxItems = 15;                     // 8-CTA clusters of this footprint resident on a B200 (tools/probe_cluster.cu)
 
 struct CDir {
@@ -84,7 +84,8 @@ struct ClusterP {
   int4* tab;                   // [items][max_levels + 1] per level: first position, rows, first operand row, level start
   unsigned int* flags;         // [items][8] projection chunks whose states each CTA of the cluster has published
   long long* trace;            // optional [levels][256][16] clock64 stamps per (level, CTA): 0 start, 1 gathered, 2 exchanged,
-                               // 3 projected + cells done, 4 level closed
+                               // 3 projected + cells done, 4 level closed, 5 copy warp: every stage started, 7 MMA warp: every
+                               // stage issued, 8 workers: accumulators of the first chunk complete
   CDir dir[DAGNN_MAX_DIRS];
   CLay lay[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
 };
@@ -92,7 +93,7 @@ struct ClusterP {
 struct CSmemTail {
   float stage[2][kWRows][kSLd];     // epilogue transpose: [accumulator][gate * 32 + unit][row of the pass]
   float bias[4][kCU];
-  uint64_t full[kCSlots], empty[kCSlots], acc_full, tmem_free;
+  uint64_t full[kCSlots], empty[kCSlots], acc_full[2], tmem_free[2];
   uint32_t tmem_slot;
   int nlong;                        // gather phase: rows of this CTA with long in-edge lists (index into the level)
   int longrow[32];
@@ -112,10 +113,14 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// address of the 16-byte granule holding k = [8 gk, 8 gk + 8) of operand row q (plane 0 = hi, 1 = lo): planes of k chunks of
-// rows, a row = 128 bytes = 64 k, granules XOR-swizzled with the row index like the shared-memory tile they are copied into
+// address of the 16-byte granule holding k = [8 gk, 8 gk + 8) of operand row q (plane 0 = hi, 1 = lo). Layout: per 64-k chunk,
+// per group of 8 rows: the hi atom (8 rows x 128 bytes, granules XOR-swizzled with the row like the shared-memory tile it is
+// copied into) then the lo atom — the rows [q0, q0 + 8 g) of one k chunk, both halves, are ONE contiguous run of 2 KB per
+// group: one bulk copy per stage, and in shared memory the hi / lo tiles are read with a 2 KB group stride.
 __device__ __forceinline__ unsigned char* oprow_ptr(unsigned char* img, int plane, int nck, long long Q, long long q, int gk) {
-  return img + ((((size_t)plane * nck + (gk >> 3)) * (size_t)Q + (size_t)q) << 7) + (((gk & 7) ^ ((int)q & 7)) << 4);
+  (void)nck;
+  return img + ((((size_t)(gk >> 3) * (size_t)(Q >> 3) + (size_t)(q >> 3)) * 2 + plane) << 10) + (((int)q & 7) << 7) +
+         (((gk & 7) ^ ((int)q & 7)) << 4);
 }
 // 8 fp16 weights W[col, 8 gk .. 8 gk + 8) from a packed projection image (pack.cu: 64-column blocks x 64-k chunks, hi then lo tile)
 __device__ __forceinline__ uint4 packed_w8(const __half* img, int nck, int col, int gk, int plane) {
@@ -307,13 +312,6 @@ __device__ __forceinline__ int lower_bound_dev(const int* a, int n, int key) {  
   return lo;
 }
 
-// issuer-side state of the operand slots. The 96 KB operand region is cut per projection chunk into as many stages (hi tile
-// + lo tile of the chunk's rows, rounded up to 32) as fit: chunks of <= 32 rows get 12 stages — every k chunk of both
-// operands lands in its own stage, all bulk copies of the chunk are in flight at once — full 128-row chunks cycle through 3.
-struct Slots {
-  uint32_t full_par, empty_par;      // bit s: parity of the next wait on full[s]; parity of the next commit on empty[s]
-};
-
 __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_constant__ ClusterP P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -335,8 +333,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < kCSlots; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    mbar_init(&S.acc_full, 1);
-    mbar_init(&S.tmem_free, kCWorkWarps);
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.acc_full[s], 1); mbar_init(&S.tmem_free[s], kCWorkWarps); }
     S.nlong = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -430,11 +427,12 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   cluster_sync_all();
 
   const uint32_t wih_s = smem_u32(Wih), ring_s = smem_u32(Ring);
-  uint32_t ct = 0;                       // projection chunks done so far
-  Slots SL = {0u, 0u};
+  uint32_t ct = 0;                       // projection chunks done so far (every role keeps its own count; they agree per level)
+  uint32_t full_par = 0u, load_par = 0u; // MMA warp: bit s = parity of its next wait on full[s]; copy warp: bit s = copies into slot s so far & 1
   // half-warp index in the cluster, rank-minor: a short level spreads over the CTAs
-  const int ghw = ((lane >> 4) * kCWorkWarps + warp) * kCS + rank;
+  const int ghw = ((lane >> 4) * kCWorkWarps + (warp & (kCWorkWarps - 1))) * kCS + rank;
   constexpr int kHalfWarps = kCS * kCWorkWarps * 2;            // 128
+  constexpr int kMmaWarp = kCWorkWarps, kCopyWarp = kCWorkWarps + 1;
 
   // layer 0: the operand rows of level 0's inputs (those of level l + 1 are converted during level l)
   if (first_layer && L > 0) {
@@ -455,101 +453,126 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     const int nchunks = (n + kRC - 1) / kRC;
     const bool exchange = l > 0;           // the aggregates of this level travel through global memory to every CTA
 
-    // one projection chunk from the issuer's side. part 1 = bulk copies of every stage that has its own slot + the MMAs of
-    // the input operand; part 2 (after the exchange barrier for chunk 0) = the aggregate operand
-    auto issue_chunk = [&](int c, int part_lo, int part_hi) {
-      const int r0 = c * kRC;
-      const int rows = min(kRC, n - r0);
-      const int rp = (rows + 31) & ~31;                        // rows of a stage tile
-      const uint32_t stage_bytes = 2u * (uint32_t)rp * tc::ROW_BYTES;
-      const int nslots = rp <= 32 ? 12 : rp <= 64 ? 6 : rp <= 96 ? 4 : 3;
-      const uint32_t bytes = (uint32_t)((rows + 7) & ~7) * tc::ROW_BYTES;
-      const int ns = nck_in + (l > 0 ? P.nckh : 0);
-      const uint32_t idesc = uni(tc::instr_desc_f16(128, (rows + 15) & ~15));
-      auto load_stage = [&](int k) {
-        const int slot = k % nslots;
-        if (k >= nslots) {                                     // the MMAs of stage k - nslots read this slot: committed, wait
-          mbar_wait(&S.empty[slot], ((SL.empty_par >> slot) & 1u) ^ 1u);
+    // The projection of a level is a linear sequence of stages j = chunk * ns + k (k < nck_in: a 64-k chunk of the input
+    // operand, then the 64-k chunks of the aggregate operand). The COPY warp starts one bulk copy per stage (hi + lo tile of
+    // the chunk's rows) into slot j % nslots as soon as the MMAs that read the slot before have completed; the MMA warp waits
+    // for the bytes, issues the 12 MMAs of the stage into the accumulator set of the chunk and commits (frees the slot; the
+    // last stage of a chunk also signals the accumulators). Chunks alternate between two accumulator sets: the epilogue of one
+    // overlaps the MMAs of the next. Levels of <= 32 rows cut the operand region into 12 slots (the whole chunk in flight at
+    // once), the others into 6. Stage cursors advance without a runtime division (walked ~8 times per level by each role).
+    const int ns = nck_in + (l > 0 ? P.nckh : 0);
+    const int rp = n <= 32 ? 32 : kRC;                         // rows of a stage tile
+    const int nslots = n <= 32 ? 12 : 6;
+    const uint32_t stage_bytes = 2u * (uint32_t)rp * tc::ROW_BYTES;
+    const int total_stages = nchunks * ns;
+    struct Cur { int j, c, k, slot; };
+    auto advance = [&](Cur& q) {
+      ++q.j;
+      if (++q.k == ns) { q.k = 0; ++q.c; }
+      if (++q.slot == nslots) q.slot = 0;
+    };
+    Cur cur = {0, 0, 0, 0};
+    // ---- copy warp: stages [cur.j, j_hi)
+    auto copy_stages = [&](int j_hi) {
+#pragma unroll 1
+      for (; cur.j < j_hi; advance(cur)) {
+        const int c = cur.c, k = cur.k, slot = cur.slot;
+        const int r0 = c * kRC;
+        const uint32_t bytes = (uint32_t)((min(kRC, n - r0) + 7) >> 3) * 2048u;     // hi + lo atom of every 8-row group
+        // MMAs of the stage that used this slot before (this level): committed by the MMA warp, wait for them to finish
+        if (cur.j >= nslots) mbar_wait(&S.empty[slot], ((load_par >> slot) & 1u) ^ 1u);
+        if (k == 0 && !first_layer) {
+          // the input rows of this chunk are the states the cluster of the layer below has published: every one of its CTAs
+          // counts the chunks whose unit slice it has stored (same level tables on both sides, so chunk numbers agree)
+          const unsigned int* fl = P.flags + (size_t)(item - P.dirs * P.G) * kCS + (lane & (kCS - 1));
+          const unsigned int want = ct + (unsigned int)c + 1u;
+          while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= want)) {}
+          asm volatile("fence.proxy.async;" ::: "memory");
         }
         if (elect_one()) {
           const bool is_in = k < nck_in;
           const int kc = is_in ? k : k - nck_in;
-          unsigned char* img = is_in ? inimg : Lp.mimg;
-          const int nck = is_in ? nck_in : P.nckh;
-          const unsigned char* src_hi = img + ((((size_t)0 * nck + kc) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
-          const unsigned char* src_lo = img + ((((size_t)1 * nck + kc) * (size_t)P.Q + (size_t)(q0 + r0)) << 7);
-          unsigned char* dst = Ring + (size_t)slot * stage_bytes;
-          mbar_expect_tx(&S.full[slot], 2 * bytes);
-          bulk_g2s(dst, src_hi, bytes, &S.full[slot]);
-          bulk_g2s(dst + (size_t)rp * tc::ROW_BYTES, src_lo, bytes, &S.full[slot]);
+          const unsigned char* src = (is_in ? inimg : Lp.mimg) + (((size_t)kc * (size_t)(P.Q >> 3) + (size_t)((q0 + r0) >> 3)) << 11);
+          mbar_expect_tx(&S.full[slot], bytes);
+          bulk_g2s(Ring + (size_t)slot * stage_bytes, src, bytes, &S.full[slot]);
         }
         __syncwarp();
-      };
-      if (part_lo == 0 && !first_layer) {
-        // the input rows of this chunk are the states the cluster of the layer below has published: every one of its CTAs
-        // counts the chunks whose unit slice it has stored (same level tables on both sides, so chunk numbers agree)
-        const unsigned int* fl = P.flags + (size_t)(item - P.dirs * P.G) * kCS + (lane & (kCS - 1));
-        while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= ct + 1u)) {}
-        asm volatile("fence.proxy.async;" ::: "memory");
+        load_par ^= 1u << slot;
       }
-      if (part_lo == 0) {
-        // the previous chunk's MMAs are done (its accumulators were complete before its epilogue began, and this chunk is only
-        // issued behind that epilogue's end or the level barrier): every slot is free, the region may be re-cut
-        if (ct >= 1) mbar_wait(&S.tmem_free, (ct - 1) & 1u);
-        tc::fence_after_sync();
-      }
-      const int k_lo = part_lo == 0 ? 0 : nck_in, k_hi = part_hi == 2 ? ns : nck_in;
-      // a stage may be copied once the stage that used its slot before (k - nslots) has had its MMAs issued: at the start of
-      // a part that holds for every k < k_lo + nslots — with 12 slots the whole chunk is in flight at once
-      int loaded = k_lo;
-      while (loaded < k_hi && loaded < k_lo + nslots) load_stage(loaded++);
+    };
+    // ---- MMA warp: stages [cur.j, j_hi)
+    auto mma_stages = [&](int j_hi) {
 #pragma unroll 1
-      for (int k = k_lo; k < k_hi; ++k) {
-        const int slot = k % nslots;
-        mbar_wait(&S.full[slot], (SL.full_par >> slot) & 1u);
-        SL.full_par ^= 1u << slot;
+      for (; cur.j < j_hi; advance(cur)) {
+        const int c = cur.c, k = cur.k, slot = cur.slot;
+        const uint32_t cc = ct + (uint32_t)c, set = cc & 1u;
+        mbar_wait(&S.full[slot], (full_par >> slot) & 1u);
+        full_par ^= 1u << slot;
+        if (k == 0 && cc >= 2) mbar_wait(&S.tmem_free[set], ((cc >> 1) - 1u) & 1u);   // this set's previous chunk has been read
         tc::fence_after_sync();
         const bool is_in = k < nck_in;
         const int kc = is_in ? k : k - nck_in;
         const int Kop = is_in ? Kin : P.Kh;
         const int nks = min(4, (Kop - 64 * kc) >> 4);
+        const int rows = min(kRC, n - c * kRC);
+        const uint32_t idesc = uni(tc::instr_desc_f16(128, (rows + 15) & ~15));
         const uint32_t sb = uni(ring_s + (uint32_t)slot * stage_bytes);
-        const uint64_t bh = tc::smem_desc(sb), bl = tc::smem_desc(sb + (uint32_t)rp * tc::ROW_BYTES);
+        const uint64_t bh = tc::smem_desc(sb, 2048u), bl = tc::smem_desc(sb + 1024u, 2048u);
+        const uint32_t fresh = uni(kc == 0 ? 0u : 1u);
+        // 12 MMAs per full stage, issued back to back by one elected lane from warp-uniform operands and fully unrolled:
+        // anything else (a counted loop, lane == 0 instead of elect.sync) costs 65-85 cycles per issue instead of 42-50
+        // (tools/ubench_mma.cu, profiles/r1h_ubench_mma.txt)
         if (is_in) {
           const uint32_t a0 = uni(wih_s + (uint32_t)kc * kWChunkBytes), a1 = uni(wih_s + (uint32_t)(nck_in + kc) * kWChunkBytes);
           const uint64_t ah = tc::smem_desc(a0), al = tc::smem_desc(a1);
-          const uint32_t acc = uni(tmem + (uint32_t)kColAccX);
-          if (elect_one()) {
+          const uint32_t acc = uni(tmem + (uint32_t)kColAcc + set * (uint32_t)kColSet);
+          if (nks == 4) {
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? fresh : 1u);
+                tc::mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
+                tc::mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1u);
+              }
+            }
+          } else if (elect_one()) {
             for (int ks = 0; ks < nks; ++ks) {
-              tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_f16(acc, ah + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? fresh : 1u);
               tc::mma_f16(acc, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
               tc::mma_f16(acc, al + 2 * ks, bh + 2 * ks, idesc, 1u);
             }
           }
         } else {
-          const uint32_t acc = uni(tmem + (uint32_t)kColAccH);
+          const uint32_t acc = uni(tmem + (uint32_t)(kColAcc + kColAccH) + set * (uint32_t)kColSet);
           const uint32_t ah = uni(tmem + (uint32_t)(kColWhi + 32 * kc)), al = uni(tmem + (uint32_t)(kColWlo + 32 * kc));
-          if (elect_one()) {
+          if (nks == 4) {
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, ks == 0 ? fresh : 1u);
+                tc::mma_f16_ts(acc, ah + 8 * ks, bl + 2 * ks, idesc, 1u);
+                tc::mma_f16_ts(acc, al + 8 * ks, bh + 2 * ks, idesc, 1u);
+              }
+            }
+          } else if (elect_one()) {
             for (int ks = 0; ks < nks; ++ks) {
-              tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_f16_ts(acc, ah + 8 * ks, bh + 2 * ks, idesc, ks == 0 ? fresh : 1u);
               tc::mma_f16_ts(acc, ah + 8 * ks, bl + 2 * ks, idesc, 1u);
               tc::mma_f16_ts(acc, al + 8 * ks, bh + 2 * ks, idesc, 1u);
             }
           }
         }
-        if (elect_one()) tc::commit(&S.empty[slot]);
-        __syncwarp();
-        SL.empty_par ^= 1u << slot;
-        // keep the slots busy: the next stage goes where stage k was once its MMAs are done
-        if (loaded < k_hi && loaded - nslots <= k) load_stage(loaded++);
-      }
-      if (part_hi == 2) {
-        if (elect_one()) tc::commit(&S.acc_full);
+        if (elect_one()) {
+          tc::commit(&S.empty[slot]);
+          if (k == ns - 1) tc::commit(&S.acc_full[set]);
+        }
         __syncwarp();
       }
     };
+    // stages that do not wait for the exchange barrier: the input part of the first chunk (everything at level 0)
+    const int early = exchange ? nck_in : total_stages;
 
-    // ---------------- gather phase (workers) / input part of the first chunk (issuer) ----------------
+    // ---------------- gather phase (workers) / input part of the first chunk (copy + MMA warps) ----------------
     if (warp < kCWorkWarps) {
       // short levels: the dependent-load chains of the two jobs would add up in a warp, so warps 0..3 gather and warps 4..7
       // convert the next level's input rows at the same time
@@ -620,8 +643,10 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         if (tid == 0) S.nlong = 0;
       }
       if (first_layer && !split && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
+    } else if (warp == kCopyWarp) {
+      copy_stages(early);
     } else {
-      issue_chunk(0, 0, exchange ? 1 : 2);
+      mma_stages(early);
     }
     if (tr && tid == 0) tr[1] = clock64();
     if (exchange) {
@@ -630,26 +655,36 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     }
     if (tr && tid == 0) tr[2] = clock64();
     // ---------------- projection + cell ----------------
+    if (warp == kCopyWarp) {
+      copy_stages(total_stages);
+      if (tr && lane == 0) tr[5] = clock64();
+      ct += (uint32_t)nchunks;
+    } else if (warp == kMmaWarp) {
+      mma_stages(total_stages);
+      if (tr && lane == 0) tr[7] = clock64();
+      ct += (uint32_t)nchunks;
+    } else {
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      const int r0 = c * kRC;
-      const int rows = min(kRC, n - r0);
-      if (warp == kCWorkWarps) {
-        if (c == 0) { if (exchange) issue_chunk(0, 1, 2); }
-        else issue_chunk(c, 0, 2);
-      } else {
+      for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * kRC;
+        const int rows = min(kRC, n - r0);
         // ---- worker warps: epilogue. TMEM lane = gate * 32 + unit, column = row of the chunk.
-        mbar_wait(&S.acc_full, ct & 1u);
-        tc::fence_after_sync();
-        const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
+        const uint32_t set = ct & 1u;
         const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
         const int u = u0 + 4 * ug;
+        const bool in_row = u + 4 <= P.Hq;
+        float4 mv_next = make_float4(0.f, 0.f, 0.f, 0.f);      // the aggregate's slice of the first pass: in flight while the MMAs run
+        if (l > 0 && in_row && row < rows && 4 * ug < P.U) mv_next = ldcg4(Lp.m32 + (size_t)(pos0 + r0 + row) * P.ldh + u);
+        mbar_wait(&S.acc_full[set], (ct >> 1) & 1u);
+        tc::fence_after_sync();
+        if (tr && tid == 0 && c == 0) tr[8] = clock64();
+        const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
 #pragma unroll 1
         for (int s0 = 0; s0 < rows; s0 += kSub) {
           if (qd < 3) {
             float v[32];
             if (acc_id == 0 || l > 0) {
-              tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)((acc_id ? kColAccH : kColAccX) + s0), v);
+              tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(kColAcc + (acc_id ? kColAccH : 0) + s0) + set * (uint32_t)kColSet, v);
               tc::wait_ld();
             } else {
 #pragma unroll
@@ -663,9 +698,8 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
           const int rr = s0 + row;
           if (rr < rows && 4 * ug < P.U) {
             const int p = pos0 + r0 + rr;
-            float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool in_row = u + 4 <= P.Hq;
-            if (l > 0 && in_row) mv = ldcg4(Lp.m32 + (size_t)p * P.ldh + u);
+            const float4 mv = mv_next;
+            if (l > 0 && in_row && rr + kSub < rows) mv_next = ldcg4(Lp.m32 + (size_t)(p + kSub) * P.ldh + u);
             float o[4];
             const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
@@ -695,11 +729,11 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         }
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.tmem_free);
+        if (lane == 0) mbar_arrive(&S.tmem_free[set]);
         // behind the last pass's closing workers_sync: the whole CTA has stored its slice of the chunk's states
         if (has_next && tid == 0) st_release_u32(P.flags + (size_t)item * kCS + rank, ct + 1u);
+        ct += 1;
       }
-      ct += 1;
     }
     if (tr && tid == 0) tr[3] = clock64();
     // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
@@ -723,7 +757,7 @@ namespace dagnn {
 // rows of an operand-row plane: every (group, level) segment starts on a multiple of 8 rows, groups are spaced by 8 L rows
 static int64_t cluster_q_rows(int64_t N, int32_t max_levels, int dirs, int layers) {
   const int gcap = kCMaxItems / (dirs * layers) > 0 ? kCMaxItems / (dirs * layers) : 1;
-  return N + 8 * (int64_t)max_levels * gcap + 64;
+  return (N + 8 * (int64_t)max_levels * gcap + 64 + 7) / 8 * 8;
 }
 
 bool cluster_path_supported(int dirs, int layers, int Din, int H, int nvid) {

@@ -37,9 +37,10 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c8) {
 }
 
 // ---- descriptors
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+// group_stride = bytes between consecutive groups of 8 rows (the descriptor's stride-byte-offset): 1024 for a dense tile
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t group_stride = GROUP_BYTES) {
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);                     // start address, LBO (unused for SW128 K-major)
-  const uint32_t hi = (uint32_t)(GROUP_BYTES >> 4) | (1u << 14) | (2u << 29);    // SBO = 1024 B, version = 1, SWIZZLE_128B
+  const uint32_t hi = (group_stride >> 4) | (1u << 14) | (2u << 29);             // SBO, version = 1, SWIZZLE_128B
   return ((uint64_t)hi << 32) | lo;
 }
 __host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) {

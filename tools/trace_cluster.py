@@ -1,5 +1,6 @@
 """Profiling helper: per-level timeline of the cluster-resident sweep (clock64 stamps written by k_sweep_cluster; slots in
-dagnn_b200/csrc/sweep_cluster.cu: 0 level start, 1 gathered, 2 exchanged, 3 projected + cells done, 4 level closed).
+dagnn_b200/csrc/sweep_cluster.cu: 0 level start, 1 gathered, 2 exchanged, 3 projected + cells done, 4 level closed, 5 / 7 / 8
+copy warp done / MMA warp done / first accumulators complete).
     python tools/trace_cluster.py [workload]      (GPU box)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -49,7 +50,11 @@ for c in range(items * G_):
         cl = (tc[:, 4] - tc[:, 3]).max() / MHZ
         lv = (tc[:, 4].max() - tc[:, 0].min()) / MHZ
         tot += lv
-        print("%3d | %6.2f %6.2f %6.2f %6.2f | %7.2f | %8.1f" % (l, ga, ex, pr, cl, lv, (t[0] - t00) / MHZ))
+        iss = ""
+        if t[5] > 0 and t[7] > 0 and t[8] > 0:
+            iss = " | after barrier: copies started %5.2f, MMAs issued %5.2f, first accumulators seen %5.2f, last cells stored %5.2f" % (
+                (t[5] - t[2]) / MHZ, (t[7] - t[2]) / MHZ, (t[8] - t[2]) / MHZ, (t[3] - t[2]) / MHZ)
+        print("%3d | %6.2f %6.2f %6.2f %6.2f | %7.2f | %8.1f%s" % (l, ga, ex, pr, cl, lv, (t[0] - t00) / MHZ, iss))
     print("    sum of level durations %.1f us" % tot)
 end = tr[:L, :ncta, 4].max()
 print("first start -> last close: %.1f us" % ((end - t00) / MHZ))
