@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdagnn_sm100.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "sweep_cluster.cu", "tc_selftest.cu"]
+SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "sweep_cluster.cu", "sweep_bwd.cu", "gemm.cu", "tc_selftest.cu"]
 HEADERS = ["common.cuh", "sync.cuh", "tc.cuh"]
 
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 vp = C.c_void_p
 
@@ -57,6 +57,29 @@ class DagnnSweepArgs(C.Structure):
     ]
 
 
+class DagnnCellParams(C.Structure):
+    _fields_ = [("weight_ih", vp), ("weight_hh", vp), ("bias_ih", vp), ("bias_hh", vp), ("attn_w", vp), ("edge_w", vp),
+                ("Dq", C.c_int32), ("reserved", C.c_int32)]
+
+
+class DagnnCellGrads(C.Structure):
+    _fields_ = [("weight_ih", vp), ("weight_hh", vp), ("bias_ih", vp), ("bias_hh", vp), ("attn_w", vp), ("edge_w", vp)]
+
+
+class DagnnSweepBwdArgs(C.Structure):
+    _fields_ = [
+        ("sched", C.POINTER(DagnnSchedule)),
+        ("num_layers", C.c_int32), ("Din", C.c_int32), ("H", C.c_int32), ("nvid", C.c_int32),
+        ("X", vp), ("ldx", C.c_int64),
+        ("Hs", (vp * MAX_LAYERS) * MAX_DIRS), ("dHs", (vp * MAX_LAYERS) * MAX_DIRS), ("ldh", C.c_int64),
+        ("params", (DagnnCellParams * MAX_LAYERS) * MAX_DIRS), ("grads", (DagnnCellGrads * MAX_LAYERS) * MAX_DIRS),
+        ("dX", vp), ("lddx", C.c_int64),
+        ("use_edge_attr", C.c_int32), ("num_levels", C.c_int32),
+        ("lvl_off_host", vp * MAX_DIRS),
+        ("workspace", vp), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class DagnnReadoutBlock(C.Structure):
     _fields_ = [
         ("src", vp), ("ld", C.c_int64), ("width", C.c_int32), ("index_mode", C.c_int32), ("dir", C.c_int32),
@@ -81,6 +104,14 @@ EXPORTS = {
     "dagnn_sweep_forward_f32": (C.c_int, [C.POINTER(DagnnSweepArgs), vp]),
     "dagnn_tc_selftest_f16x3": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "dagnn_tc_selftest_ts": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dagnn_linear_f32": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "dagnn_gemm_f32": (C.c_int, [vp, C.c_int64, C.c_int32, vp, C.c_int64, C.c_int32, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, vp]),
+    "dagnn_sweep_backward_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
+    "dagnn_sweep_backward_f32": (C.c_int, [C.POINTER(DagnnSweepBwdArgs), vp]),
+    "dagnn_readout_backward_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.POINTER(vp), C.c_int32, C.c_int32,
+                                             vp, vp, C.c_int64, vp]),
+    "dagnn_embed_backward_f32": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, vp, vp, vp, vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),
     "dagnn_states_to_node_order_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.c_int32, vp, C.c_int64, C.c_int32, vp,

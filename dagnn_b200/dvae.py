@@ -12,9 +12,10 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import runtime as rt
 from .data import DagBatch, collate_dvae
-from .ogb import AttnConv, NA_ATTN_H, P_MAX, _PackedCacheMixin, _forward_only_guard
+from .ogb import AttnConv, NA_ATTN_H, P_MAX, _PackedCacheMixin, _needs_grad
 
 
 class _DVAEParams(nn.Module):
@@ -117,12 +118,38 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
         ng = int(ng) if ng is not None else int(G.batch[-1].item()) + 1
         return rt.Schedule.build(G.edge_index, lv, ids, None, G.batch, ng, max_levels)
 
-    def node_states(self, G, sched=None, max_levels: int = 256):
-        sched = sched if sched is not None else self.build_schedule(G, max_levels)
+    # ------------------------------------------------------------------ hooks of autograd.SweepReadoutFn
+    def _sweep_dims(self):
+        return self.emb_dim, self.hidden_dim, self.num_layers, (self.num_nodes if self._VID else 0), False
+
+    def _cell_params(self):
+        out = []
+        for d in self.dirs:
+            for i in range(self.num_layers):
+                cell, ag_ = getattr(self, "cells_%d" % d)[i], getattr(self, "node_aggr_%d" % d)[i]
+                out += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag_.attn_lin.weight, ag_.attn_lin.bias]
+        return out
+
+    def _pack(self, device) -> rt.PackedParams:
         cells = [getattr(self, "cells_%d" % d) for d in self.dirs]
         aggrs = [getattr(self, "node_aggr_%d" % d) for d in self.dirs]
         nv = self.num_nodes if self._VID else 0
-        packed = self._packed.update(cells, aggrs, self.emb_dim, self.hidden_dim, nv, False, G.x.device)
+        return self._packed.update(cells, aggrs, self.emb_dim, self.hidden_dim, nv, False, device)
+
+    def _readout_blocks(self, G, X, Hs):
+        """last node of every graph (forward states) [|| first node (backward states)] over all layers (dvae/dagnn.py:147-161)."""
+        H, blocks, col = self.hidden_dim, [], 0
+        for l in range(self.num_layers):
+            blocks.append(dict(src=Hs[0, l], width=H, index_mode=1, dir=0, filter=rt.FILTER_LAST, out_col=col)); col += H
+        if self.bidirectional:
+            for l in range(self.num_layers):
+                blocks.append(dict(src=Hs[1, l], width=H, index_mode=1, dir=1, filter=rt.FILTER_FIRST, out_col=col)); col += H
+        return blocks, "add", col
+
+    def node_states(self, G, sched=None, max_levels: int = 256):
+        sched = sched if sched is not None else self.build_schedule(G, max_levels)
+        nv = self.num_nodes if self._VID else 0
+        packed = self._pack(G.x.device)
         X = G.x.float().contiguous()
         Hs = rt.sweep(sched, X, packed, self.emb_dim, self.hidden_dim, self.num_layers, nv, False)
         return X, Hs, sched
@@ -130,21 +157,18 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
     def forward(self, G):
         """dvae/dagnn.py:99-175 / dvae/dagnn_bn.py:98-168 with out_pool_all=False: last node of every graph
         (forward states) [‖ first node (backward states)] over all layers -> out_linear / hg_unify."""
-        _forward_only_guard(self)
         G = G.to(self.get_device())
-        def run(max_levels):
-            X, Hs, sched = self.node_states(G, None, max_levels)
-            H, blocks, col = self.hidden_dim, [], 0
-            for l in range(self.num_layers):
-                blocks.append(dict(src=Hs[0, l], width=H, index_mode=1, dir=0, filter=rt.FILTER_LAST, out_col=col)); col += H
-            if self.bidirectional:
-                for l in range(self.num_layers):
-                    blocks.append(dict(src=Hs[1, l], width=H, index_mode=1, dir=1, filter=rt.FILTER_FIRST, out_col=col)); col += H
-            return rt.readout(sched, blocks, "add", col, X.device), sched
-        hcat = rt.run_checked(run)
+        if _needs_grad(self):
+            hcat = ag.SweepReadoutFn.apply(self, G, G.x.float().contiguous(), *self._cell_params())
+        else:
+            def run(max_levels):
+                X, Hs, sched = self.node_states(G, None, max_levels)
+                blocks, pool, width = self._readout_blocks(G, X, Hs)
+                return rt.readout(sched, blocks, pool, width, X.device), sched
+            hcat = rt.run_checked(run)
         if self.bidirectional:
-            return self.hg_unify(hcat)
-        return self.out_linear(hcat) if self.num_layers > 1 else hcat
+            return ag.linear(hcat, self.hg_unify[0])
+        return ag.linear(hcat, self.out_linear) if self.num_layers > 1 else hcat
 
     def encode(self, G):
         """dvae/dagnn.py:177-184: list of graphs -> (mu, logvar)."""
@@ -152,7 +176,7 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
             G = [G]
         b = G[0] if (len(G) == 1 and hasattr(G[0], "batch")) else collate_dvae(G)
         Hg = self(b)
-        return self.fc1(Hg), self.fc2(Hg)
+        return ag.linear(Hg, self.fc1), ag.linear(Hg, self.fc2)
 
     def _collate_fn(self, G):
         return [g.clone() if isinstance(g, DagBatch) else g for g in G]

@@ -9,7 +9,8 @@ on the CUDA device; returns a list of `max_seq_len` tensors `[B, num_vocab]` (or
 Scope: the default aggregator `agg="attn_h"` with GRU cells (`recurr=1`), uni/bidirectional,
 `out_wx`, `out_pool_all`, `out_pool` in {max, mean, add}. Other aggregators / `agg_x` / `recurr=0` /
 `out_pool="attn"` raise NotImplementedError at construction (§8f row 4), they never fall back to eager torch.
-Forward only: calling it with autograd enabled on trainable parameters raises (backward = §8f row 1).
+Training: with autograd enabled the forward runs through `dagnn_b200.autograd` (EmbedFn, SweepReadoutFn, LinearFn), whose
+backward is the library's reverse-level BPTT — `loss.backward()` works as in main_pyg.py:55-65.
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import autograd as ag
 from . import runtime as rt
 
 NA_ATTN_H = "attn_h"
@@ -34,8 +36,10 @@ class ASTNodeEncoder(nn.Module):
         self.depth_encoder = nn.Embedding(self.max_depth + 1, emb_dim)
 
     def forward(self, x, depth):
-        return rt.embed(x, depth, self.type_encoder.weight, self.attribute_encoder.weight, self.depth_encoder.weight,
-                        self.max_depth)
+        T, A, P = self.type_encoder.weight, self.attribute_encoder.weight, self.depth_encoder.weight
+        if torch.is_grad_enabled() and (T.requires_grad or A.requires_grad or P.requires_grad):
+            return ag.EmbedFn.apply(x, depth, T, A, P, self.max_depth)
+        return rt.embed(x, depth, T, A, P, self.max_depth)
 
 
 class AttnConv(nn.Module):
@@ -66,10 +70,8 @@ class _PackedCacheMixin(object):
         return super().train(mode)
 
 
-def _forward_only_guard(module: nn.Module):
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise RuntimeError("dagnn_b200 implements the forward pass only (backward is SURVEY.md §8f row 1): call the "
-                           "module under torch.no_grad() / torch.inference_mode(). There is no autograd fallback.")
+def _needs_grad(module: nn.Module) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
 
 
 class DAGNN(_PackedCacheMixin, nn.Module):
@@ -156,8 +158,22 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         Hs = rt.sweep(sched, X, packed, self.emb_dim, self.hidden_dim, self.num_layers, 0, self.w_edge_attr)
         return X, Hs, sched
 
-    def readout(self, G, X, Hs, sched) -> torch.Tensor:
-        """dagnn.py:184-202."""
+    # ------------------------------------------------------------------ hooks of autograd.SweepReadoutFn
+    def _sweep_dims(self):
+        return self.emb_dim, self.hidden_dim, self.num_layers, 0, self.w_edge_attr
+
+    def _cell_params(self):
+        out = []
+        for d in self.dirs:
+            for i in range(self.num_layers):
+                cell, ag_ = getattr(self, "cells_%d" % d)[i], getattr(self, "node_aggr_%d" % d)[i]
+                out += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, ag_.attn_lin.weight, ag_.attn_lin.bias]
+                if self.w_edge_attr:
+                    out += [ag_.edge_encoder.weight, ag_.edge_encoder.bias]
+        return out
+
+    def _readout_blocks(self, G, X, Hs):
+        """dagnn.py:184-202 as a list of pooled column blocks."""
         H, Lr, blocks = self.hidden_dim, self.num_layers, []
         lvl = [G._bi_layer_idx0, G._bi_layer_idx1]
         col = 0
@@ -175,7 +191,12 @@ class DAGNN(_PackedCacheMixin, nn.Module):
             for d in self.dirs:
                 for l in range(Lr):
                     blocks.append(dict(src=Hs[d, l], width=H, index_mode=1, dir=d, out_col=col, **filt)); col += H
-        return rt.readout(sched, blocks, self.out_pool, col, X.device)
+        return blocks, self.out_pool, col
+
+    def readout(self, G, X, Hs, sched) -> torch.Tensor:
+        """dagnn.py:184-202."""
+        blocks, pool, width = self._readout_blocks(G, X, Hs)
+        return rt.readout(sched, blocks, pool, width, X.device)
 
     def forward_readout(self, G):
         """The north-star hot path: encoder -> schedule -> level sweeps (both directions) -> pooled readout.
@@ -183,16 +204,26 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         collater, which drops empty shards (tg/dataloader.py:29-31)."""
         if G.x.shape[0] == 0:
             return torch.zeros(0, self.out_hidden_dim, device=G.x.device, dtype=torch.float32)
+        if _needs_grad(self):            # training: the same stages as autograd Functions (backward = reverse-level BPTT)
+            X = self.encoder(G.x, G.node_depth.view(-1, ))
+            if X.shape[1] != self.emb_dim:
+                raise ValueError("encoder produced width %d, emb_dim is %d" % (X.shape[1], self.emb_dim))
+            return ag.SweepReadoutFn.apply(self, G, X, *self._cell_params())
 
         def run(max_levels):
             X, Hs, sched = self.node_states(G, None, max_levels)
             return self.readout(G, X, Hs, sched), sched
         return rt.run_checked(run)
 
+    def _head(self, layer, out):
+        """nn.Linear (or Sequential(Linear, ReLU) when num_vocab == 1, dagnn.py:106-108) through dagnn_linear_f32."""
+        if isinstance(layer, nn.Sequential):
+            return layer[1](ag.linear(out, layer[0]))
+        return ag.linear(out, layer)
+
     def forward(self, G):
-        _forward_only_guard(self)
         out = self.forward_readout(G)
         out = self.dropout(out)
         if self.num_class > 0:
-            return self.graph_pred_linear(out)
-        return [self.graph_pred_linear_list[i](out) for i in range(self.max_seq_len)]
+            return self._head(self.graph_pred_linear, out)
+        return [self._head(self.graph_pred_linear_list[i], out) for i in range(self.max_seq_len)]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 7
+#define DAGNN_ABI_VERSION 8
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -231,6 +231,75 @@ int dagnn_readout_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* block
  *          R <= 64, N % 16 == 0, 16 <= N <= 256, K % 16 == 0, K <= 256. */
 int dagnn_tc_selftest_f16x3(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
 int dagnn_tc_selftest_ts(const float* W, const float* X, float* C, int32_t R, int32_t N, int32_t K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Small dense layers on the tensor cores (fp16 x 3 split, fp32-grade accuracy), no cuBLAS:
+ *   dagnn_linear_f32   y[M, N] = x[M, K] w[N, K]^T + bias[N]      nn.Linear.forward — the heads (ogbg-code/model/dagnn.py:209-215),
+ *                      out_linear / hg_unify (dvae/dagnn.py:156,161), fc1 / fc2 (:183). bias may be NULL.
+ *   dagnn_gemm_f32     C[M, N] (+)= A B^T with each operand either [rows, K] row-major (kmajor = 1) or its transposed view
+ *                      [K, rows] (kmajor = 0): the backward of the above (dx = dy w: B = w as [K = N_out, rows = K_in];
+ *                      dw = dy^T x: both operands transposed views) and of the GRU cells.
+ * --------------------------------------------------------------------------------------------------------- */
+int dagnn_linear_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int32_t M,
+                     int32_t N, int32_t K, void* stream);
+int dagnn_gemm_f32(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int32_t b_kmajor, float* C, int64_t ldc,
+                   int32_t M, int32_t N, int32_t K, int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward of the path: what torch.autograd derives from ogbg-code/model/dagnn.py:141-202 and
+ * ogbg-code/utils.py:26-28, so that loss.backward() (main_pyg.py:55-65, dvae/train.py:255-264) runs on this library.
+ *   dagnn_readout_backward_f32  gradient of the pooled readout into the gradient buffers of its sources. grad_blocks[k] describes
+ *                               block k as in the forward with `src` = the GRADIENT buffer (same shape / ld as the forward source,
+ *                               accumulated with atomicAdd: zero it first), fwd_src[k] = the forward source, out / dout [B, ldo].
+ *   dagnn_sweep_backward_f32    reverse-level BPTT through GRU cells and attention. dHs[d][i] holds d loss / d H[d][i] (position
+ *                               order) on entry and is clobbered; parameter gradients are overwritten; dX (node order, may be
+ *                               NULL) is accumulated (+=). Needs HOST copies of the level offsets (the forward's schedule has
+ *                               been finalized by then). The query part of attn_lin.weight gets zeros (its exact gradient).
+ *   dagnn_embed_backward_f32    dT[x0] += dX, dA[x1] += dX, dP[min(depth, max_depth)] += dX (atomicAdd; zero the tables' gradients first).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct DagnnCellParams {      /* raw parameters of one (direction, layer): device pointers, row-major like torch */
+  const float* weight_ih;             /* [3H, Din_i]                                  */
+  const float* weight_hh;             /* [3H, H]                                      */
+  const float* bias_ih;               /* [3H]                                         */
+  const float* bias_hh;               /* [3H]                                         */
+  const float* attn_w;                /* attn_lin.weight [1, Dq + H + nvid]           */
+  const float* edge_w;                /* edge_encoder.weight [H, 2] or NULL           */
+  int32_t Dq;
+  int32_t reserved;
+} DagnnCellParams;
+typedef struct DagnnCellGrads {       /* same shapes; all written by dagnn_sweep_backward_f32 */
+  float* weight_ih;
+  float* weight_hh;
+  float* bias_ih;
+  float* bias_hh;
+  float* attn_w;
+  float* edge_w;                      /* NULL when there is no edge encoder */
+} DagnnCellGrads;
+typedef struct DagnnSweepBwdArgs {
+  const DagnnSchedule* sched;
+  int32_t num_layers, Din, H, nvid;
+  const float* X;                     /* [N, ldx] node order (the forward's input) */
+  int64_t ldx;
+  const float* Hs[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];   /* forward states, position order, [N, ldh] */
+  float* dHs[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];        /* in: gradient wrt the states; clobbered    */
+  int64_t ldh;
+  DagnnCellParams params[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
+  DagnnCellGrads grads[DAGNN_MAX_DIRS][DAGNN_MAX_LAYERS];
+  float* dX;                          /* [N, lddx] node order, accumulated; NULL = not needed */
+  int64_t lddx;
+  int32_t use_edge_attr;
+  int32_t num_levels;                 /* summary[0] of the schedule                                */
+  const int32_t* lvl_off_host[DAGNN_MAX_DIRS];         /* HOST copies of sched->lvl_off[d], num_levels + 1 entries */
+  void* workspace;                    /* dagnn_sweep_backward_workspace_bytes(), 256-byte aligned  */
+  size_t workspace_bytes;
+} DagnnSweepBwdArgs;
+
+size_t dagnn_sweep_backward_workspace_bytes(int32_t Din, int32_t H, int32_t nvid, int64_t N, int64_t E);
+int dagnn_sweep_backward_f32(const DagnnSweepBwdArgs* args, void* stream);
+int dagnn_readout_backward_f32(const DagnnSchedule* sched, const DagnnReadoutBlock* grad_blocks, const float* const* fwd_src, int32_t nblocks,
+                               int32_t pool, const float* out, const float* dout, int64_t ldo, void* stream);
+int dagnn_embed_backward_f32(const int64_t* x, const int64_t* depth, int max_depth, int64_t n_types, int64_t n_attrs, int64_t N, int D,
+                             const float* dX, int64_t ldx, float* d_type_tab, float* d_attr_tab, float* d_depth_tab, void* stream);
 
 /* Un-permute states for inspection / tests: dst[v,:] = src[pos[dir][v],:]  (fp32 [N,H]) */
 int dagnn_states_to_node_order_f32(const DagnnSchedule* sched, int32_t dir, const float* src, int64_t lds,
