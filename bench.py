@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — graphs/s of the DAGNN layer-wise forward (encoder -> schedule -> level sweeps -> readout).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|na|bn|big]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|na|bn|big] [--train-step]
 
 Workload at N GPUs (weak scaling): BASELINE.json configs[1] — synthetic ogbg-code2-shaped batch, DAGNN 2 layers,
 emb_dim = hidden = 256, bidirectional, attn_h, max-pool readout, 128 graphs PER GPU (global batch 128·N, built
@@ -17,6 +17,8 @@ A step = one forward of the hot path over one batch.
   cpu_baseline : the oracle port of the reference's CPU path (oracle/dagnn_oracle.py — the reference is Python and
           needs PyG, which does not exist on the box) on the same batch, host cores of this box.
 `--impl reference` times that CPU port alone (rank 0 only) and prints the same line with "impl": "reference".
+`--train-step` times a whole training step instead (forward + multi-head cross entropy + backward + ONE NCCL all-reduce of the
+flat fp32 gradient buffer + Adam step; BASELINE configs[4] with --workload c5): same line plus a "train" object.
 """
 import argparse
 import json
@@ -43,10 +45,12 @@ WORKLOADS = {
                desc="ogbg-code2-shaped synthetic, DAGNN 5-layer emb_dim=hidden=300 bidirectional, batch=128/GPU (1024 over 8)"),
     "big": dict(graphs=4096, emb=256, hid=256, layers=2, bidir=True, kind="code2",
                 desc="ogbg-code2-shaped synthetic, config-2 model at batch=4096/GPU (per-level kernel HBM evidence)"),
-    "na": dict(graphs=32, emb=8, hid=501, layers=2, bidir=False, kind="NA",
-               desc="ENAS-shaped 8-node DAGs (random well-formed rows), D-VAE DAGNN hs=501 2-layer unidirectional, batch=32"),
-    "bn": dict(graphs=128, emb=10, hid=501, layers=2, bidir=True, kind="BN",
-               desc="BN-shaped 10-node DAGs (random well-formed rows), D-VAE DAGNN_BN hs=501 2-layer bidirectional, batch=128"),
+    "na": dict(graphs=32, emb=8, hid=501, layers=2, bidir=False, kind="NA", rows="na_real_hs501",
+               desc="NA data set rows 1000..1031 of dvae/data/final_structures6.txt (8-node ENAS DAGs), D-VAE DAGNN hs=501 2-layer "
+                    "unidirectional, batch=32"),
+    "bn": dict(graphs=128, emb=10, hid=501, layers=2, bidir=True, kind="BN", rows="bn_real_hs501",
+               desc="BN data set rows 0..127 of dvae/data/asia_200k.txt (10-node Bayesian networks), D-VAE DAGNN_BN hs=501 2-layer "
+                    "bidirectional, batch=128"),
 }
 SEED = 20262
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
@@ -61,6 +65,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
+    ap.add_argument("--train-step", action="store_true", help="time forward + loss + backward + gradient all-reduce + optimizer step")
     return ap.parse_args()
 
 
@@ -69,7 +74,13 @@ def build_workload(wl, world):
     from dagnn_b200 import data as D
     if wl["kind"] == "code2":
         return D.make_code2_batch(wl["graphs"] * world, SEED)
-    return D.make_random_dvae_batch(wl["graphs"] * world, SEED, wl["kind"])
+    # real rows of the reference's data files, carried by the golden fixtures (tests/golden/*.npz, key "rows"); more ranks
+    # than one repeat them
+    z = np.load(os.path.join(ROOT, "tests", "golden", wl["rows"] + ".npz"), allow_pickle=False)
+    rows = json.loads(str(z["rows"]))
+    dec = D.decode_enas_row if wl["kind"] == "NA" else D.decode_bn_row
+    need = wl["graphs"] * world
+    return D.collate_dvae([dec(rows[k % len(rows)]) for k in range(need)])
 
 
 def build_module(wl):
@@ -168,14 +179,18 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep launch from the committed `ncu --set full` capture
-    (profiles/traffic.json: bytes per launch, keyed by workload) or None."""
+def ncu_traffic(workload, kernel):
+    """(dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, where the number comes from) — from the committed
+    `ncu --set full` capture (profiles/traffic.json: bytes per launch keyed by workload, tagged with the kernel and the commit it
+    was captured at), or (None, reason). A capture of another kernel than the one this run launches is not reported."""
     try:
-        j = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return float(j[workload]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+        j = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        if j.get("kernel") != kernel:
+            return None, "no ncu capture of %s for this workload (profiles/traffic.json holds %s)" % (kernel, j.get("kernel"))
+        return float(j["dram_bytes_per_launch"]), "ncu --set full, %s at commit %s (profiles/traffic.json; 1 GPU, whole batch)" % (
+            kernel, j.get("commit", "?"))
+    except Exception as e:
+        return None, "profiles/traffic.json: %s" % (e,)
 
 
 def measured_peaks():
@@ -216,7 +231,7 @@ def cpu_baseline(p, B, wl, budget_s=25.0):
             ts.append(time.perf_counter() - t0)
     med = float(np.median(ts))
     return {"value": ng / med, "unit": "graphs/s", "cores": int(torch.get_num_threads()), "host_cpus": os.cpu_count(),
-            "kind": "port", "sample": "%d full-batch forwards of the same %d-graph batch (oracle/dagnn_oracle.py, torch CPU "
+            "kind": "port (reference-on-shim unavailable on the box)", "sample": "%d full-batch forwards of the same %d-graph batch (oracle/dagnn_oracle.py, torch CPU "
             "fp32, eval/no_grad), median %.3f s" % (len(ts), ng, med)}
 
 
@@ -259,7 +274,9 @@ def run_reference(args, wl, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": wl["graphs"] * world},
             "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": int(torch.get_num_threads()), "host_cpus": os.cpu_count(),
-                             "kind": "port", "sample": "each step = one forward over the first %d graphs of the %d-graph "
+                             "kind": "port (the reference's files need torch_geometric, which exists neither on the box nor in "
+                                     "this image: oracle/dagnn_oracle.py, pinned against the reference on the PyG shim)",
+                             "sample": "each step = one forward over the first %d graphs of the %d-graph "
                              "batch (oracle/dagnn_oracle.py; smaller batches make the reference's O(N*E) edge scan cheaper "
                              "per graph, i.e. this favours the reference)" % (n_s, ng)},
             "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,6 +285,17 @@ def run_reference(args, wl, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ main
+def gather_stats(x, world, dev):
+    """[value of every rank] (one tiny all_gather; outside the timed regions)."""
+    import torch.distributed as dist
+    if world == 1:
+        return [float(x)]
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def main():
     args = parse()
     wl = WORKLOADS[args.workload]
@@ -292,7 +320,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     Bglobal = build_workload(wl, world)
+    # depth-aware graph shards (data.shard_graph_ids): the deepest graphs go to different ranks and take fewer nodes with them
     Bcpu, my_graphs = sharding.shard_for_rank(Bglobal, rank, world)
+    if Bcpu is None:
+        raise SystemExit("rank %d owns no graph (more ranks than graphs)" % rank)
     n_graphs_local = int(Bcpu.num_graphs)
     m_cpu = build_module(wl)
     p_cpu = {k: v.detach().clone() for k, v in m_cpu.state_dict().items()}
@@ -326,30 +357,30 @@ def main():
         return sum(a.elapsed_time(b) for a, b in ev), wall
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return max(gather_stats(x, world, dev))
+
+    if args.train_step:
+        return run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks, barrier)
 
     with torch.no_grad():
-        # ---- parity gate (small slice vs the oracle) before any timing is accepted
+        # ---- parity gate before any timing is accepted: the WHOLE shard of rank 0 against the oracle
         if rank == 0:
-            small = D.select_graphs(Bcpu, range(min(4, n_graphs_local)))
-            ref = oracle_forward(p_cpu, small, wl)
-            got = hot_path(m, small.to(dev), wl).cpu()
+            ref = oracle_forward(p_cpu, Bcpu, wl)
+            got = hot_path(m, G, wl).cpu()
             err = (got - ref).abs().max().item()
             if not err <= 1e-4:
-                raise SystemExit("parity gate failed: max-abs err %g vs the oracle" % err)
+                raise SystemExit("parity gate failed: max-abs err %g vs the oracle on the %d-graph shard of rank 0" % (err, n_graphs_local))
+            parity = {"checked_graphs": n_graphs_local, "max_abs_err_vs_oracle": err, "bar": 1e-4}
 
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
         # ---- value: inputs resident in HBM
         n0 = _lib.launch_count()
-        ms_dev, _ = timed(lambda: hot_path(m, G, wl), args.steps, args.warmup)
+        ms_dev_local, _ = timed(lambda: hot_path(m, G, wl), args.steps, args.warmup)
         launches = (_lib.launch_count() - n0) // (args.steps + args.warmup) * args.steps
-        ms_dev = max_over_ranks(ms_dev)
+        ms_dev_all = gather_stats(ms_dev_local, world, dev)
+        ms_dev = max(ms_dev_all)
 
         # ---- e2e: pinned host batch -> H2D -> forward -> D2H readout, per step
         out_host = None
@@ -378,11 +409,7 @@ def main():
         sweep_launches = (_lib.launch_count() - n1) // (args.steps + 3)
         clk = clocks.stop() if rank == 0 else None
 
-    total_graphs = wl["graphs"] * world
-    if world > 1:
-        cnt = torch.tensor([n_graphs_local], device=dev)
-        dist.all_reduce(cnt)
-        total_graphs = int(cnt.item())
+    total_graphs = int(sum(gather_stats(n_graphs_local, world, dev)))
     value = total_graphs * args.steps / (ms_dev * 1e-3)
     e2e = total_graphs * args.steps / (ms_e2e * 1e-3)
     alg_bytes, e_prime = sweep_algorithmic_bytes(Bcpu, wl)
@@ -391,7 +418,15 @@ def main():
     H, layers, dirs = wl["hid"], wl["layers"], (2 if wl["bidir"] else 1)
     N = int(Bcpu.x.shape[0])
     flops = sum(6 * H * ((wl["emb"] if i == 0 else H) + H) for i in range(layers)) * N * dirs
+    node_steps = N * dirs * layers
+    cluster_path = H <= 256 and wl["emb"] <= 256 and node_steps <= 600000 and os.environ.get("DAGNN_SWEEP_PATH") != "grid"
+    kernel = "k_sweep_cluster (cluster-resident level sweep)" if cluster_path else "k_sweep (grid-wide level sweep)"
+    per_rank = {"nodes": [int(v) for v in gather_stats(N, world, dev)], "graphs": [int(v) for v in gather_stats(n_graphs_local, world, dev)],
+                "levels": [int(v) for v in gather_stats(int(sched.num_levels[0]), world, dev)],
+                "forward_ms": [v / args.steps for v in ms_dev_all],
+                "sweep_ms": [v / args.steps for v in gather_stats(ms_sweep, world, dev)]}
     if rank == 0:
+        traffic, traffic_src = ncu_traffic(args.workload, kernel.split(" ")[0])
         line = {
             "metric": "graphs/sec forward", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -400,21 +435,87 @@ def main():
                        "nodes_rank0": N, "edges_rank0": int(Bcpu.edge_index.shape[1]), "levels": int(sched.num_levels[0]),
                        "l2": "flushed between steps (256 MiB fill)" if not args.no_flush else "not flushed",
                        "timed_region": "node encoder + schedule build (incl. its one D2H of level offsets) + level sweeps + readout",
-                       "parallelism": "graph-sharded dp%d, no forward collective" % world},
+                       "parallelism": "graph-sharded dp%d (depth-aware shards), no forward collective" % world},
             "e2e": {"value": e2e, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_sweep (persistent level sweep, %d launch per forward)" % sweep_launches, "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                         "peak_source": peak_src, "algorithmic_bytes_per_sweep": int(alg_bytes),
+            "roofline": {"kernel": "%s, %d launch per forward" % (kernel, sweep_launches), "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_sweep": int(alg_bytes),
                          "sweep_ms": ms_sweep / args.steps, "gathered_edges": e_prime,
                          "gate_gemm_tflops_fp32": flops * args.steps / (ms_sweep * 1e-3) / 1e12},
+            "parity": parity,
+            "per_rank": per_rank,
             "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(p_cpu, Bcpu, wl)
         elif world > 1:
             line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks, barrier):
+    """forward + loss + backward + one all-reduce of the flat gradient buffer + Adam step, per step (main_pyg.py:55-65 with the
+    reference's DataParallel reduce-add, tg/data_parallel.py:59-62, replaced by NCCL)."""
+    import torch.distributed as dist
+    from dagnn_b200 import _lib, sharding
+    if wl["kind"] != "code2":
+        raise SystemExit("--train-step is defined for the code2-shaped workloads")
+    m.train()
+    params = [p for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    nb = int(Bcpu.num_graphs)
+    g = torch.Generator().manual_seed(7 + rank)
+    from dagnn_b200 import data as D
+    y = torch.randint(0, D.CODE2_NUM_VOCAB, (D.CODE2_MAX_SEQ_LEN, nb), generator=g).to(dev)
+    ev = {k: [] for k in ("fwd", "bwd", "ar", "opt")}
+    nelem = {"n": 0}
+
+    def step():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e[0].record()
+        opt.zero_grad(set_to_none=False)
+        pred = m(G)
+        loss = sum(torch.nn.functional.cross_entropy(pred[k], y[k]) for k in range(len(pred))) / len(pred)
+        e[1].record()
+        loss.backward()
+        e[2].record()
+        nelem["n"] = sharding.allreduce_gradients(params, average=True)
+        e[3].record()
+        opt.step()
+        e[4].record()
+        ev["fwd"].append((e[0], e[1])); ev["bwd"].append((e[1], e[2])); ev["ar"].append((e[2], e[3])); ev["opt"].append((e[3], e[4]))
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    ms, _ = timed(step, args.steps, args.warmup)
+    launches = (_lib.launch_count() - n0) // (args.steps + args.warmup) * args.steps
+    clk = clocks.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    parts = {k: sum(a.elapsed_time(b) for a, b in v[-args.steps:]) / args.steps for k, v in ev.items()}
+    parts = {k: max_over_ranks(v) for k, v in parts.items()}
+    total_graphs = int(sum(gather_stats(nb, world, dev)))
+    grad_bytes = 4 * nelem["n"]
+    busbw = (2.0 * (world - 1) / world) * grad_bytes / (parts["ar"] * 1e-3) / 1e9 if world > 1 else None
+    if rank == 0:
+        line = {"metric": "graphs/sec training step", "value": total_graphs * args.steps / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": total_graphs,
+                           "timed_region": "zero_grad + forward (all heads) + cross entropy + backward + NCCL all-reduce of the flat fp32 "
+                                           "gradient buffer + Adam step",
+                           "parallelism": "graph-sharded dp%d; one gradient all-reduce per step" % world},
+                "gpu_launches": int(launches),
+                "train": {"forward_ms": parts["fwd"], "backward_ms": parts["bwd"], "allreduce_ms": parts["ar"], "optimizer_ms": parts["opt"],
+                          "gradient_elements": nelem["n"], "gradient_bytes": grad_bytes, "allreduce_busbw_GBs": busbw,
+                          "nvlink_pool_GBs": 725.0},
+                "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -26,6 +26,7 @@ struct GemmP {
   int a_kmajor, b_kmajor;      // 1: [rows, K] row-major; 0: [K, rows]
   int beta;                    // 1: accumulate into C
   int a_vec, b_vec;            // K-contiguous operand may be read with 16-byte loads
+  int ksplit, chunks_per;      // blockIdx.z takes 64-k chunks [z * chunks_per, (z + 1) * chunks_per); ksplit > 1: C is accumulated atomically
 };
 
 // one 64-k chunk of one operand: rows [r0, r0 + 128) x k [k0, k0 + 64) -> hi / lo tiles
@@ -78,14 +79,17 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16x3(const __grid_constant__ G
   tc::fence_after_sync();
   const uint32_t tmem = *slot;
   const int m0 = blockIdx.x * kGT, n0 = blockIdx.y * kGT;
-  const int nchunks = (P.K + 63) / 64;
+  const int all_chunks = (P.K + 63) / 64;
+  const int c_begin = blockIdx.z * P.chunks_per;
+  const int nchunks = min(P.chunks_per, all_chunks - c_begin);           // >= 1 by construction of the grid
   const uint32_t idesc = tc::instr_desc_f16(128, kGT);
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     unsigned char* st = base + (size_t)s * kGStage;
     if (c >= 2) mbar_wait(&bar[s], ((c >> 1) - 1) & 1u);       // the MMAs that read this stage two chunks ago are done
-    stage_operand(P.A, P.lda, P.M, P.K, m0, c * 64, P.a_kmajor, P.a_vec, st, st + kGT * tc::ROW_BYTES, tid);
-    stage_operand(P.B, P.ldb, P.N, P.K, n0, c * 64, P.b_kmajor, P.b_vec, st + 2 * kGT * tc::ROW_BYTES, st + 3 * kGT * tc::ROW_BYTES, tid);
+    const int k0 = (c_begin + c) * 64;
+    stage_operand(P.A, P.lda, P.M, P.K, m0, k0, P.a_kmajor, P.a_vec, st, st + kGT * tc::ROW_BYTES, tid);
+    stage_operand(P.B, P.ldb, P.N, P.K, n0, k0, P.b_kmajor, P.b_vec, st + 2 * kGT * tc::ROW_BYTES, st + 3 * kGT * tc::ROW_BYTES, tid);
     tc::fence_async_smem();
     __syncthreads();
     if (warp == 0) {
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16x3(const __grid_constant__ G
           const int col = n0 + cb * 8 + j;
           if (col < P.N) {
             float* o = P.C + (size_t)row * P.ldc + col;
-            float r = v[j] + (P.bias ? __ldg(P.bias + col) : 0.f);
-            if (P.beta) r += *o;
-            *o = r;
+            float r = v[j] + ((P.bias && blockIdx.z == 0) ? __ldg(P.bias + col) : 0.f);
+            if (P.ksplit > 1) atomicAdd(o, r);                 // C was zeroed by the launcher unless it accumulates anyway
+            else { if (P.beta) r += *o; *o = r; }
           }
         }
       }
@@ -147,7 +151,16 @@ int gemm_f16x3(const float* A, long long lda, int a_kmajor, const float* B, long
   P.a_kmajor = a_kmajor; P.b_kmajor = b_kmajor; P.beta = beta;
   P.a_vec = (a_kmajor && (lda & 3) == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
   P.b_vec = (b_kmajor && (ldb & 3) == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
-  dim3 grid((unsigned)ceil_div(M, kGT), (unsigned)ceil_div(N, kGT));
+  // few output tiles and a long contraction (weight gradients: K = number of nodes; the per-level data gradients): split K
+  // over blockIdx.z so that the grid fills the SMs; partial tiles are accumulated with atomicAdd
+  const int tiles = ceil_div(M, kGT) * ceil_div(N, kGT), chunks = ceil_div(K, 64);
+  int ksplit = 1;
+  if (tiles < 148 && chunks >= 4) ksplit = min(chunks / 2, ceil_div(296, tiles));
+  P.chunks_per = ceil_div(chunks, ksplit);
+  ksplit = ceil_div(chunks, P.chunks_per);
+  P.ksplit = ksplit;
+  if (ksplit > 1 && !beta) DAGNN_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+  dim3 grid((unsigned)ceil_div(M, kGT), (unsigned)ceil_div(N, kGT), (unsigned)ksplit);
   k_gemm_f16x3<<<grid, 256, kGSmem, st>>>(P);
   return check_launch("k_gemm_f16x3");
 }
