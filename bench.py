@@ -468,6 +468,7 @@ def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks
     m.train()
     params = [p for p in m.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3)
+    flat = sharding.FlatGradients(params)            # every .grad is a view into one buffer: the exchange is one NCCL call
     nb = int(Bcpu.num_graphs)
     g = torch.Generator().manual_seed(7 + rank)
     from dagnn_b200 import data as D
@@ -478,13 +479,13 @@ def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks
     def step():
         e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record()
-        opt.zero_grad(set_to_none=False)
+        flat.zero()
         pred = m(G)
         loss = sum(torch.nn.functional.cross_entropy(pred[k], y[k]) for k in range(len(pred))) / len(pred)
         e[1].record()
         loss.backward()
         e[2].record()
-        nelem["n"] = sharding.allreduce_gradients(params, average=True)
+        nelem["n"] = flat.allreduce(average=True)
         e[3].record()
         opt.step()
         e[4].record()

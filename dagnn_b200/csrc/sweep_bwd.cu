@@ -359,10 +359,20 @@ static BwdWs carve_bwd(void* ws, int Din, int H, int64_t N, int64_t E, int nvid)
 
 using namespace dagnn;
 
+// one scratch set per direction: the two directions are independent and run concurrently on two streams
 extern "C" size_t dagnn_sweep_backward_workspace_bytes(int32_t Din, int32_t H, int32_t nvid, int64_t N, int64_t E) {
   if (Din < 1 || H < 1 || N < 0 || E < 0 || nvid < 0) return 0;
-  return carve_bwd(nullptr, Din, H, N, E, nvid).bytes;
+  return DAGNN_MAX_DIRS * carve_bwd(nullptr, Din, H, N, E, nvid).bytes;
 }
+
+namespace {
+struct BwdStreams {                 // per device: the second direction's stream and the fork / join events
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+BwdStreams g_bwd_streams[dagnn::kMaxDevices];
+dagnn::PerDeviceOnce g_bwd_once;
+}  // namespace
 
 static int grid_for(long long work, int per_block) {
   long long b = (work + per_block - 1) / per_block;
@@ -377,11 +387,32 @@ extern "C" int dagnn_sweep_backward_f32(const DagnnSweepBwdArgs* A, void* stream
   DAGNN_REQUIRE(dirs >= 1 && dirs <= DAGNN_MAX_DIRS && layers >= 1 && layers <= DAGNN_MAX_LAYERS, "sweep backward: dirs / layers");
   DAGNN_REQUIRE(A->X && A->ldx >= Din && H >= 1 && Din >= 1 && A->ldh >= H && L >= 1 && L <= S->max_levels, "sweep backward: sizes");
   DAGNN_REQUIRE(A->workspace && ((uintptr_t)A->workspace & 255) == 0, "sweep backward: workspace must be 256-byte aligned");
-  BwdWs w = carve_bwd(A->workspace, Din, H, N, S->E, A->nvid);
-  if (A->workspace_bytes < w.bytes) return set_err(DAGNN_E_WORKSPACE, "sweep backward: workspace too small");
-  const long long ldh = A->ldh, ldg = w.ldg;
+  const size_t ws_one = carve_bwd(nullptr, Din, H, N, S->E, A->nvid).bytes;
+  if (A->workspace_bytes < dirs * ws_one) return set_err(DAGNN_E_WORKSPACE, "sweep backward: workspace too small");
+  const long long ldh = A->ldh;
   const int ldx_pos = round_up(Din, 4), ld_dinp = round_up(Din > H ? Din : H, 4);
+  // direction 1 runs on a side stream (forked from / joined into the caller's): the per-level launches of the two directions
+  // interleave on the device instead of queueing behind each other. dX is the only shared output: its two scatter-adds are
+  // ordered by the join (direction 1 adds its part on the caller's stream after the join).
+  cudaStream_t main_st = st;
+  int dev = 0;
+  if (int rc = per_device_once(g_bwd_once, &dev, [&](int dv) {
+        DAGNN_CUDA_OK(cudaStreamCreateWithFlags(&g_bwd_streams[dv].side, cudaStreamNonBlocking));
+        DAGNN_CUDA_OK(cudaEventCreateWithFlags(&g_bwd_streams[dv].fork, cudaEventDisableTiming));
+        DAGNN_CUDA_OK(cudaEventCreateWithFlags(&g_bwd_streams[dv].join, cudaEventDisableTiming));
+        return (int)DAGNN_OK;
+      }))
+    return rc;
+  const BwdStreams& bs = g_bwd_streams[dev];
+  if (dirs == 2) {
+    DAGNN_CUDA_OK(cudaEventRecord(bs.fork, main_st));
+    DAGNN_CUDA_OK(cudaStreamWaitEvent(bs.side, bs.fork, 0));
+  }
+  float* dinp1_deferred = nullptr;
   for (int d = 0; d < dirs; ++d) {
+    st = d == 0 ? main_st : bs.side;
+    BwdWs w = carve_bwd(static_cast<char*>(A->workspace) + (size_t)d * ws_one, Din, H, N, S->E, A->nvid);
+    const long long ldg = w.ldg;
     DAGNN_REQUIRE(A->lvl_off_host[d], "sweep backward: host level offsets");
     const int32_t* lo = A->lvl_off_host[d];
     for (int i = layers - 1; i >= 0; --i) {
@@ -438,9 +469,11 @@ extern "C" int dagnn_sweep_backward_f32(const DagnnSweepBwdArgs* A, void* stream
         if (i > 0) {
           k_rows_add<<<grid_for((long long)N * H, 256), 256, 0, st>>>(w.dinp, ld_dinp, A->dHs[d][i - 1], ldh, N, H);
           if (int rc = check_launch("k_rows_add")) return rc;
-        } else {
+        } else if (d == 0) {
           k_scatter_rows_add<<<grid_for((long long)N * Din, 256), 256, 0, st>>>(S->perm[d], w.dinp, ld_dinp, A->dX, A->lddx, N, Din);
           if (int rc = check_launch("k_scatter_rows_add")) return rc;
+        } else {
+          dinp1_deferred = w.dinp;               // added on the caller's stream behind the join
         }
       }
       // ---- parameter gradients
@@ -456,6 +489,14 @@ extern "C" int dagnn_sweep_backward_f32(const DagnnSweepBwdArgs* A, void* stream
       k_bwd_attn_params<<<ceil_div(pr.Dq + H + A->nvid, 256), 256, 0, st>>>(pr.attn_w, pr.Dq, H, A->nvid, ap.eattr ? pr.edge_w : nullptr, dwk, dca,
                                                                               dvid, gr.attn_w, gr.edge_w);
       if (int rc = check_launch("k_bwd_attn_params")) return rc;
+    }
+  }
+  if (dirs == 2) {
+    DAGNN_CUDA_OK(cudaEventRecord(bs.join, bs.side));
+    DAGNN_CUDA_OK(cudaStreamWaitEvent(main_st, bs.join, 0));
+    if (dinp1_deferred) {
+      k_scatter_rows_add<<<grid_for((long long)N * Din, 256), 256, 0, main_st>>>(S->perm[1], dinp1_deferred, ld_dinp, A->dX, A->lddx, N, Din);
+      if (int rc = check_launch("k_scatter_rows_add")) return rc;
     }
   }
   return DAGNN_OK;

@@ -80,3 +80,35 @@ def allreduce_gradients(params, group=None, average: bool = False) -> int:
         g.copy_(flat[off: off + n].view_as(g))
         off += n
     return int(flat.numel())
+
+
+class FlatGradients(object):
+    """One flat fp32 buffer holding every parameter gradient: `param.grad` of each parameter is a view into it (autograd
+    accumulates in place), so the per-step gradient exchange is exactly ONE collective over the buffer — no gather into a
+    temporary, no copy back. Replaces the reduce-add onto GPU 0 of the reference's DataParallel backward
+    (ogbg-code/tg/data_parallel.py:59-62). Use with `optimizer.zero_grad(set_to_none=False)` (or `zero()` here)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off: off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, group=None, average: bool = False) -> int:
+        """all-reduce(sum) of the buffer over the ranks (NCCL over NVLink on the box); returns the number of elements."""
+        _, w = rank_world(group)
+        if w > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.div_(w)
+        return self.numel

@@ -123,6 +123,13 @@ def _worker(rank, world, port, out):
         ref.load_state_dict(lin.state_dict())
         ref(full).sum().backward()
         assert n == 8 and torch.allclose(lin.weight.grad, ref.weight.grad, atol=1e-4) and torch.allclose(lin.bias.grad, ref.bias.grad)
+        # (4) the same through the flat gradient buffer (every .grad a view into it, one collective, no copies)
+        lin2 = torch.nn.Linear(3, 2)
+        lin2.load_state_dict(ref.state_dict())
+        fg = sharding.FlatGradients(lin2.parameters())
+        lin2(per_graph(mine)).sum().backward()
+        assert lin2.weight.grad.data_ptr() == fg.flat.data_ptr() and fg.allreduce() == 8
+        assert torch.allclose(lin2.weight.grad, ref.weight.grad, atol=1e-4) and torch.allclose(lin2.bias.grad, ref.bias.grad)
         out[rank] = 1
     finally:
         dist.destroy_process_group()
