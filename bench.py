@@ -473,11 +473,12 @@ def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks
     g = torch.Generator().manual_seed(7 + rank)
     from dagnn_b200 import data as D
     y = torch.randint(0, D.CODE2_NUM_VOCAB, (D.CODE2_MAX_SEQ_LEN, nb), generator=g).to(dev)
-    ev = {k: [] for k in ("fwd", "bwd", "ar", "opt")}
+    ev = {k: [] for k in ("fwd", "bwd", "wait", "ar", "opt")}
+    tiny = torch.zeros(1, device=dev)
     nelem = {"n": 0}
 
     def step():
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         e[0].record()
         flat.zero()
         pred = m(G)
@@ -485,11 +486,15 @@ def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks
         e[1].record()
         loss.backward()
         e[2].record()
+        if world > 1:
+            dist.all_reduce(tiny)                   # absorbs the skew between ranks: the next interval is the exchange alone
+        e[5].record()
         nelem["n"] = flat.allreduce(average=True)
         e[3].record()
         opt.step()
         e[4].record()
-        ev["fwd"].append((e[0], e[1])); ev["bwd"].append((e[1], e[2])); ev["ar"].append((e[2], e[3])); ev["opt"].append((e[3], e[4]))
+        ev["fwd"].append((e[0], e[1])); ev["bwd"].append((e[1], e[2])); ev["wait"].append((e[2], e[5])); ev["ar"].append((e[5], e[3]))
+        ev["opt"].append((e[3], e[4]))
 
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
@@ -513,7 +518,8 @@ def run_train_step(args, wl, m, G, Bcpu, rank, world, dev, timed, max_over_ranks
                                            "gradient buffer + Adam step",
                            "parallelism": "graph-sharded dp%d; one gradient all-reduce per step" % world},
                 "gpu_launches": int(launches),
-                "train": {"forward_ms": parts["fwd"], "backward_ms": parts["bwd"], "allreduce_ms": parts["ar"], "optimizer_ms": parts["opt"],
+                "train": {"forward_ms": parts["fwd"], "backward_ms": parts["bwd"], "rank_skew_wait_ms": parts["wait"], "allreduce_ms": parts["ar"],
+                          "optimizer_ms": parts["opt"],
                           "gradient_elements": nelem["n"], "gradient_bytes": grad_bytes, "allreduce_busbw_GBs": busbw,
                           "nvlink_pool_GBs": 725.0},
                 "clocks": clk}

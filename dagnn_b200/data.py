@@ -355,11 +355,12 @@ def shard_graph_ranges(nodes_per_graph: Sequence[int], world_size: int) -> List[
 
 
 def shard_graph_ids(nodes_per_graph: Sequence[int], world_size: int, depths: Optional[Sequence[int]] = None,
-                    level_cost_nodes: float = 100.0) -> List[np.ndarray]:
+                    level_cost_nodes: float = 200.0) -> List[np.ndarray]:
     """Graph ids of every shard. Without `depths`: the reference's contiguous node-balanced rule (`shard_graph_ranges`).
     With `depths` (levels of every graph): depth-aware balance. The sweep walks the levels of a shard one after the other, so
     a shard costs about  levels * t_level + nodes * t_node  — the deepest graph of a shard sets the first term (measured:
-    SCALE_r01.json, 97 levels on one rank against 66 on rank 0 cost 21 % at equal node counts). Graphs are dealt in order of
+    SCALE_r01.json, 97 levels on one rank against 66 on rank 0 cost 21 % at equal node counts; round 2, cluster sweep, 8 ranks:
+    t_level = 8.9 us, t_node = 0.0437 us, i.e. one level costs as much as ~200 nodes — the default of `level_cost_nodes`). Graphs are dealt in order of
     decreasing depth, each to the shard whose modelled cost  level_cost_nodes * max depth + nodes  stays smallest: the deepest
     graphs land on different shards and a shard with a deep graph gets fewer nodes. Ids inside a shard are ascending.
     Shards may be empty when there are fewer graphs than ranks."""
