@@ -81,9 +81,11 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
                     dropout, num_nodes):
         if agg != NA_ATTN_H:
             raise NotImplementedError("dagnn_b200 covers agg='attn_h' (SURVEY.md §8f row 4); got %r" % (agg,))
-        if out_pool_all or out_wx:
-            raise NotImplementedError("out_pool_all / out_wx readouts of the D-VAE models are not covered "
-                                      "(scripts/na_train.sh, bn_train.sh use neither)")
+        if out_wx:
+            raise NotImplementedError("out_wx: the reference concatenates G.x in front of the states and then feeds a layer sized "
+                                      "for the states alone (dvae/dagnn.py:163-168) — a shape error there, nothing to reproduce")
+        if out_pool_all and out_pool not in ("max", "mean", "add"):
+            raise NotImplementedError("out_pool=%r: the D-VAE files never define the attention readout (dvae/dagnn.py:86)" % (out_pool,))
         if hidden_dim != self.hs:
             raise ValueError("hidden_dim must equal hs (the GRU cells are grue_forward/backward, dagnn.py:73-75)")
         if emb_dim != self.nvt:
@@ -93,7 +95,7 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
         self.agg, self.agg_attn, self.agg_attn_x = agg, True, False
         self.bidirectional = bidirectional
         self.dirs = [0, 1] if bidirectional else [0]
-        self.out_wx, self.output_all = out_wx, out_pool_all
+        self.out_wx, self.output_all, self.out_pool = out_wx, out_pool_all, out_pool
         self.emb_dim, self.hidden_dim = emb_dim, hidden_dim
         self.out_hidden_dim = hidden_dim * num_layers
         nv = num_nodes if self._VID else 0
@@ -158,6 +160,8 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
         """dvae/dagnn.py:99-175 / dvae/dagnn_bn.py:98-168 with out_pool_all=False: last node of every graph
         (forward states) [‖ first node (backward states)] over all layers -> out_linear / hg_unify."""
         G = G.to(self.get_device())
+        if self.output_all:
+            return self._forward_pool_all(G)
         if _needs_grad(self):
             hcat = ag.SweepReadoutFn.apply(self, G, G.x.float().contiguous(), *self._cell_params())
         else:
@@ -169,6 +173,32 @@ class _DagnnDvaeBase(_PackedCacheMixin, _DVAEParams):
         if self.bidirectional:
             return ag.linear(hcat, self.hg_unify[0])
         return ag.linear(hcat, self.out_linear) if self.num_layers > 1 else hcat
+
+    def _forward_pool_all(self, G):
+        """out_pool_all=True (dvae/dagnn.py:162-172): the states of every node, all directions and layers side by side in node
+        order -> hg_unify / out_linear PER NODE -> pooled over all nodes of a graph. Forward only."""
+        if _needs_grad(self):
+            raise NotImplementedError("out_pool_all=True is covered forward-only: call under torch.no_grad()")
+
+        def run(max_levels):
+            X, Hs, sched = self.node_states(G, None, max_levels)
+            N, H, nd, nl = int(X.shape[0]), self.hidden_dim, len(self.dirs), self.num_layers
+            cat = torch.empty(N, nd * nl * H, device=X.device, dtype=torch.float32)
+            for d in range(nd):
+                for l in range(nl):
+                    col = (d * nl + l) * H
+                    rt.check(rt.lib().dagnn_states_to_node_order_f32(rt.C.byref(sched.c), d, Hs[d, l].data_ptr(), Hs.stride(2), H,
+                                                                     cat.data_ptr() + 4 * col, cat.stride(0), rt._stream()),
+                             "dagnn_states_to_node_order_f32")
+            if self.bidirectional:
+                per_node = ag.linear(cat, self.hg_unify[0])
+            elif nl > 1:
+                per_node = ag.linear(cat, self.out_linear)
+            else:
+                per_node = cat
+            blocks = [dict(src=per_node, width=int(per_node.shape[1]), index_mode=0, filter=rt.FILTER_ALL, out_col=0)]
+            return rt.readout(sched, blocks, self.out_pool, int(per_node.shape[1]), X.device), sched
+        return rt.run_checked(run)
 
     def encode(self, G):
         """dvae/dagnn.py:177-184: list of graphs -> (mu, logvar)."""

@@ -7,8 +7,8 @@ Same constructor signature, same parameter names/shapes (checkpoints of the refe
 on the CUDA device; returns a list of `max_seq_len` tensors `[B, num_vocab]` (or `[B, num_class]`).
 
 Scope: the default aggregator `agg="attn_h"` with GRU cells (`recurr=1`), uni/bidirectional,
-`out_wx`, `out_pool_all`, `out_pool` in {max, mean, add}. Other aggregators / `agg_x` / `recurr=0` /
-`out_pool="attn"` raise NotImplementedError at construction (§8f row 4), they never fall back to eager torch.
+`out_wx`, `out_pool_all`, `out_pool` in {max, mean, add, attn}. Other aggregators / `agg_x` / `recurr=0` raise
+NotImplementedError at construction (§8f row 4), they never fall back to eager torch.
 Training: with autograd enabled the forward runs through `dagnn_b200.autograd` (EmbedFn, SweepReadoutFn, LinearFn), whose
 backward is the library's reverse-level BPTT — `loss.backward()` works as in main_pyg.py:55-65.
 """
@@ -89,8 +89,8 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         if agg != NA_ATTN_H or agg_x or not recurr:
             raise NotImplementedError("dagnn_b200 covers agg='attn_h', agg_x=False, recurr=1 (SURVEY.md §8f row 4); "
                                       "got agg=%r agg_x=%r recurr=%r" % (agg, agg_x, recurr))
-        if out_pool not in (P_MAX, P_MEAN, P_ADD):
-            raise NotImplementedError("out_pool=%r is not covered (max / mean / add are)" % (out_pool,))
+        if out_pool not in (P_MAX, P_MEAN, P_ADD, P_ATTN):
+            raise ValueError("out_pool=%r (max / mean / add / attn)" % (out_pool,))
         if encoder is None:
             raise NotImplementedError("pass encoder=ASTNodeEncoder(...) (main_pyg.py:248,396-401); EmbeddingBag "
                                       "encoders (init_encoder, dagnn.py:218-223) are not covered")
@@ -119,6 +119,11 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         for i in self.dirs:
             setattr(self, "cells_{}".format(i), nn.ModuleList(
                 [nn.GRUCell(emb_dim if l == 0 else hidden_dim, hidden_dim) for l in range(num_layers)]))
+        if out_pool == P_ATTN:
+            # dagnn.py:88-91,114-117: Linear(d, 1) scores softmaxed over a dimension of size 1 — every weight is exactly 1, the
+            # readout is a plain add-pool. The layer exists for checkpoint compatibility; its gradient is zero.
+            d_ = int(self.out_hidden_dim / 2) if self.bidirectional and not self.output_all else self.out_hidden_dim
+            self.self_attn_linear_out = nn.Linear(d_, 1)
         self.dropout = nn.Dropout(dropout)
         if self.num_class > 0:
             self.graph_pred_linear = nn.Linear(self.out_hidden_dim, self.num_class)
@@ -191,7 +196,7 @@ class DAGNN(_PackedCacheMixin, nn.Module):
             for d in self.dirs:
                 for l in range(Lr):
                     blocks.append(dict(src=Hs[d, l], width=H, index_mode=1, dir=d, out_col=col, **filt)); col += H
-        return blocks, self.out_pool, col
+        return blocks, (P_ADD if self.out_pool == P_ATTN else self.out_pool), col
 
     def readout(self, G, X, Hs, sched) -> torch.Tensor:
         """dagnn.py:184-202."""

@@ -183,6 +183,9 @@ def level_sweep(x, edge_index, bi_layer_index, p: Dict[str, torch.Tensor], num_l
 
 
 def _pool(h, batch, kind, num_graphs):
+    if kind == "attn":
+        # dagnn.py:114-117: softmax over a dimension of size 1 — every weight is exactly 1.0 — then global_add_pool
+        kind = "add"
     idx = batch.view(-1, 1).expand_as(h)
     if kind == "max":
         out = h.new_full((num_graphs, h.shape[1]), float("-inf")).scatter_reduce(0, idx, h, reduce="amax",
@@ -239,8 +242,8 @@ def ogb_forward(p: Dict[str, torch.Tensor], G, num_layers=2, bidirectional=True,
 
 
 def dvae_forward(p: Dict[str, torch.Tensor], G, num_layers=2, bidirectional=False, num_nodes=8, vid=True,
-                 trace: Optional[dict] = None):
-    """dvae/dagnn.py:99-175 (vid=True, NA) / dvae/dagnn_bn.py:98-168 (vid=False, BN), out_pool_all=False."""
+                 trace: Optional[dict] = None, out_pool_all=False, out_pool="max"):
+    """dvae/dagnn.py:99-175 (vid=True, NA) / dvae/dagnn_bn.py:98-168 (vid=False, BN); out_pool_all=True: :162-172."""
     dirs = [0, 1] if bidirectional else [0]
     hidden = p["grue_forward.0.weight_hh"].shape[1]
     q = dict(p)
@@ -252,6 +255,13 @@ def dvae_forward(p: Dict[str, torch.Tensor], G, num_layers=2, bidirectional=Fals
     H = level_sweep(G.x, G.edge_index, G.bi_layer_index, q, num_layers, dirs, hidden,
                     vid_nodes=num_nodes if vid else 0, trace=trace)
     n = G.x.shape[0]
+    if out_pool_all:
+        cat = torch.cat([H[d][l] for d in range(len(dirs)) for l in range(num_layers)], dim=-1)
+        if bidirectional:
+            cat = F.linear(cat, p["hg_unify.0.weight"], p["hg_unify.0.bias"])
+        elif num_layers > 1:
+            cat = F.linear(cat, p["out_linear.weight"], p["out_linear.bias"])
+        return _pool(cat, G.batch, out_pool, int(G.batch.max()) + 1), H
     first = torch.arange(0, n, num_nodes)
     last = first + (num_nodes - 1)
     if bidirectional:

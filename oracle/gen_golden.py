@@ -47,6 +47,9 @@ OGB_CASES = [
     # reference: its head is sized for one direction's width more than the readout produces)
     dict(name="ogb_code2_h72_l3_mean_all", gen=("code2", 4, 20265), emb=48, hid=72, layers=3, bidir=True, out_wx=False,
          pool_all=1, pool="mean", wea=True, num_class=0, wseed=14),
+    # out_pool="attn": Linear(d, 1) scores softmaxed over a size-1 dimension = add-pool (dagnn.py:114-117)
+    dict(name="ogb_rand_attn_pool", gen=("rand", 5, 23), emb=16, hid=24, layers=2, bidir=True, out_wx=False,
+         pool_all=0, pool="attn", wea=True, num_class=0, wseed=16),
 ]
 
 DVAE_CASES = [
@@ -59,6 +62,11 @@ DVAE_CASES = [
          states=False),
     dict(name="bn_real_unidir_hs40", kind="BN", rows=("asia_200k.txt", 300, 24), hs=40, layers=2, bidir=False, wseed=12),
     dict(name="na_real_unidir_l3_hs36", kind="NA", rows=("final_structures6.txt", 2000, 24), hs=36, layers=3, bidir=False, wseed=15),
+    # out_pool_all=True: hg_unify per node, then pooled over all nodes of a graph (dvae/dagnn_bn.py:153-165)
+    dict(name="bn_real_pool_all_mean_hs40", kind="BN", rows=("asia_200k.txt", 500, 20), hs=40, layers=2, bidir=True, wseed=17,
+         pool_all=True, pool="mean"),
+    dict(name="na_real_pool_all_max_hs32", kind="NA", rows=("final_structures6.txt", 2500, 12), hs=32, layers=2, bidir=False, wseed=18,
+         pool_all=True, pool="max"),
 ]
 
 
@@ -156,7 +164,7 @@ def gen_dvae(case):
     # ctor exactly as dvae/train.py:160-172
     m = cls(nvt, case["hs"], case["hs"], nvt, nvt, 0, 1, hs=case["hs"], nz=56, num_nodes=nvt,
             agg="attn_h", num_layers=case["layers"], bidirectional=case["bidir"], out_wx=False,
-            out_pool_all=False, out_pool="max", dropout=0.0)
+            out_pool_all=case.get("pool_all", False), out_pool=case.get("pool", "max"), dropout=0.0)
     D.deterministic_init_(m, case["wseed"])
     m.eval()
     data_list = [Data(x=g.x.clone(), edge_index=g.edge_index.clone(), bi_layer_index=g.bi_layer_index.clone())

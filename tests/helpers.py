@@ -45,14 +45,14 @@ def dvae_module_from_meta(meta, device=None):
     nvt = 8 if meta["kind"] == "NA" else 10
     cls = dvae.DAGNN if meta["kind"] == "NA" else dvae.DAGNN_BN
     m = cls(nvt, meta["hs"], meta["hs"], nvt, nvt, 0, 1, hs=meta["hs"], nz=56, num_nodes=nvt, agg="attn_h",
-            num_layers=meta["layers"], bidirectional=meta["bidir"], out_wx=False, out_pool_all=False, out_pool="max",
-            dropout=0.0)
+            num_layers=meta["layers"], bidirectional=meta["bidir"], out_wx=False, out_pool_all=meta.get("pool_all", False),
+            out_pool=meta.get("pool", "max"), dropout=0.0)
     D.deterministic_init_(m, meta["wseed"])
     m.eval()
     return m.to(device) if device is not None else m
 
 
 OGB_GOLDEN = ["ogb_rand_bidir", "ogb_rand_unidir3", "ogb_rand_noattr_mean", "ogb_rand_wx_add_cls", "ogb_code2_small",
-              "ogb_code2_h300x5", "ogb_rand_h30_l1_add", "ogb_code2_h72_l3_mean_all"]
+              "ogb_code2_h300x5", "ogb_rand_h30_l1_add", "ogb_code2_h72_l3_mean_all", "ogb_rand_attn_pool"]
 DVAE_GOLDEN = ["na_real_hs64", "na_real_hs501", "na_real_bidir_hs48", "bn_real_hs64", "bn_real_hs501",
-               "bn_real_unidir_hs40", "na_real_unidir_l3_hs36"]
+               "bn_real_unidir_hs40", "na_real_unidir_l3_hs36", "bn_real_pool_all_mean_hs40", "na_real_pool_all_max_hs32"]

@@ -46,10 +46,11 @@ def test_dvae_oracle_matches_reference_fixture(name):
     nvt = 8 if meta["kind"] == "NA" else 10
     trace = {}
     with torch.no_grad():
+        pool = dict(out_pool_all=meta.get("pool_all", False), out_pool=meta.get("pool", "max"))
         out, H = O.dvae_forward(p, B, num_layers=meta["layers"], bidirectional=meta["bidir"], num_nodes=nvt,
-                                vid=(meta["kind"] == "NA"), trace=trace)
+                                vid=(meta["kind"] == "NA"), trace=trace, **pool)
         mu, logvar = O.dvae_encode(p, B, num_layers=meta["layers"], bidirectional=meta["bidir"], num_nodes=nvt,
-                                   vid=(meta["kind"] == "NA"))
+                                   vid=(meta["kind"] == "NA"), **pool)
     np.testing.assert_allclose(out.numpy(), z["out"], atol=TOL, rtol=0)
     np.testing.assert_allclose(mu.numpy(), z["mu"], atol=TOL, rtol=0)
     np.testing.assert_allclose(logvar.numpy(), z["logvar"], atol=TOL, rtol=0)
