@@ -82,7 +82,8 @@ struct ClusterP {
   const int* summary;          // [0] levels, [2] status, [3] node ids are not the identity
   const int* gptr;             // [B+1]
   int4* tab;                   // [items][max_levels + 1] per level: first position, rows, first operand row, level start
-  unsigned int* flags;         // [items][8] projection chunks whose states each CTA of the cluster has published
+  unsigned int* flags;         // [2][kCMaxItems][8] per CTA of every cluster: projection chunks whose states it has published; chunks
+                               // whose aggregates it has gathered (pipelined levels)
   long long* trace;            // optional [levels][256][16] clock64 stamps per (level, CTA): 0 start, 1 gathered, 2 exchanged,
                                // 3 projected + cells done, 4 level closed, 5 copy warp: every stage started, 7 MMA warp: every
                                // stage issued, 8 workers: accumulators of the first chunk complete
@@ -452,6 +453,9 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     if (n == 0) break;                     // a group without nodes at this level has none at deeper ones
     const int nchunks = (n + kRC - 1) / kRC;
     const bool exchange = l > 0;           // the aggregates of this level travel through global memory to every CTA
+    const bool pipelined = exchange && n > kCS * kCWorkWarps * 2;               // more rows than half-warps in the cluster (see below)
+    unsigned int* mflag = P.flags + (size_t)(kCMaxItems + item) * kCS;          // chunks of aggregates gathered, per CTA of this cluster
+    const int ns_gate = pipelined ? nck_in : -1;                                // copy warp: stage k == ns_gate waits for the counters
 
     // The projection of a level is a linear sequence of stages j = chunk * ns + k (k < nck_in: a 64-k chunk of the input
     // operand, then the 64-k chunks of the aggregate operand). The COPY warp starts one bulk copy per stage (hi + lo tile of
@@ -485,6 +489,13 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
           // the input rows of this chunk are the states the cluster of the layer below has published: every one of its CTAs
           // counts the chunks whose unit slice it has stored (same level tables on both sides, so chunk numbers agree)
           const unsigned int* fl = P.flags + (size_t)(item - P.dirs * P.G) * kCS + (lane & (kCS - 1));
+          const unsigned int want = ct + (unsigned int)c + 1u;
+          while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= want)) {}
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        if (k == ns_gate) {
+          // pipelined level: the aggregate rows of this chunk are there once every CTA of the cluster has counted it
+          const unsigned int* fl = mflag + (lane & (kCS - 1));
           const unsigned int want = ct + (unsigned int)c + 1u;
           while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= want)) {}
           asm volatile("fence.proxy.async;" ::: "memory");
@@ -569,172 +580,210 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         __syncwarp();
       }
     };
-    // stages that do not wait for the exchange barrier: the input part of the first chunk (everything at level 0)
-    const int early = exchange ? nck_in : total_stages;
+    // Levels of more than 128 rows run PIPELINED: the gather proceeds in rounds of 128 rows (one per half-warp of the cluster =
+    // two projection chunks); after a round every CTA publishes "chunks gathered" through a release counter in global memory,
+    // the copy warps poll the eight counters before copying the aggregate stages of a chunk — no cluster barrier in between —
+    // and the worker warps run the cells of round t - 1 behind the gather of round t: gather, copies, MMAs and cells of
+    // different chunks overlap. Short levels keep the single exchange barrier (one round trip less on the critical path).
+    // stages that wait for nothing of this level: the input part of the first chunk (everything at level 0; in pipelined levels
+    // the copy warp gates the aggregate stages itself)
+    const int early = (exchange && !pipelined) ? nck_in : total_stages;
 
-    // ---------------- gather phase (workers) / input part of the first chunk (copy + MMA warps) ----------------
-    if (warp < kCWorkWarps) {
-      // short levels: the dependent-load chains of the two jobs would add up in a warp, so warps 0..3 gather and warps 4..7
-      // convert the next level's input rows at the same time
-      const bool split = first_layer && exchange && n <= kHalfWarps / 2 && Tn.y <= kHalfWarps / 2;
-      const int ghw_s = (((lane >> 4) * (kCWorkWarps / 2) + (warp & 3)) * kCS + rank);      // half-warp index among 64
-      if (split && warp >= kCWorkWarps / 2) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw_s, kHalfWarps / 2, hl);
-      if (exchange) {
-        const int first = split ? (warp < kCWorkWarps / 2 ? ghw_s : n) : ghw;
-        const int stride = split ? kHalfWarps / 2 : kHalfWarps;
-        for (int r = first; __any_sync(0xffffffffu, r < n); r += stride) {
-          const bool on = r < n;
-          const int p = pos0 + (on ? r : 0);
-          int e0 = 0, e1 = 0;
-          if (on) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
-          bool lng = e1 - e0 > kLongEdges;                     // split over the CTA's half-warps below, if the list has room
-          int slot = 0;
-          if (lng && hl == 0) slot = atomicAdd(&S.nlong, 1);
-          slot = __shfl_sync(0xffffffffu, slot, lane & 16);
-          if (lng) {
-            if (slot < kMaxLong) { if (hl == 0) S.longrow[slot] = r; e1 = e0; } else lng = false;
+    // ---- worker pieces
+    // rows r = first, first + stride, ... < r_end of this level: aggregates (and softmax) of the nodes, long in-edge lists
+    // split over the CTA's half-warps afterwards
+    auto gather_rows = [&](int first, int stride, int r_end) {
+      for (int r = first; __any_sync(0xffffffffu, r < r_end); r += stride) {
+        const bool on = r < r_end;
+        const int p = pos0 + (on ? r : 0);
+        int e0 = 0, e1 = 0;
+        if (on) { e0 = D.rowptr[p]; e1 = D.rowptr[p + 1]; }
+        bool lng = e1 - e0 > kLongEdges;                     // split over the CTA's half-warps below, if the list has room
+        int slot = 0;
+        if (lng && hl == 0) slot = atomicAdd(&S.nlong, 1);
+        slot = __shfl_sync(0xffffffffu, slot, lane & 16);
+        if (lng) {
+          if (slot < kMaxLong) { if (hl == 0) S.longrow[slot] = r; e1 = e0; } else lng = false;
+        }
+        GAcc A;
+        gacc_init(A);
+        gather_edges(P, D, Lp, e0, e1, 0, lstart, hl, wk, ca0, ca1, A);
+        if (on && !lng) finish_row(P, Lp, p, (long long)q0 + r, hl, A);
+      }
+      workers_sync();
+      const int nl = min(S.nlong, kMaxLong);
+      float* part = &S.stage[0][0][0];                       // [16 half-warps][kPartLd]
+      for (int j = 0; j < nl; ++j) {
+        const int r = S.longrow[j];
+        const int p = pos0 + r;
+        const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
+        const int hw = 2 * warp + (lane >> 4);
+        GAcc A;
+        gacc_init(A);
+        gather_edges(P, D, Lp, e0 + hw, e1, 4, lstart, hl, wk, ca0, ca1, A);
+        float* mine = part + hw * kPartLd;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(mine + 16 * hl + 4 * q) = A.m[q];
+        if (hl == 0) { mine[256] = A.mx; mine[257] = A.den; }
+        workers_sync();
+        {                                                    // thread = k: merge the 16 partial softmax states
+          float M = -INFINITY;
+#pragma unroll
+          for (int h = 0; h < 16; ++h) M = nanmax(M, part[h * kPartLd + 256]);
+          float den = 0.f, acc = 0.f;
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const float w = expf(part[h * kPartLd + 256] - M);
+            den = fmaf(part[h * kPartLd + 257], w, den);
+            acc = fmaf(part[h * kPartLd + tid], w, acc);
           }
-          GAcc A;
-          gacc_init(A);
-          gather_edges(P, D, Lp, e0, e1, 0, lstart, hl, wk, ca0, ca1, A);
-          if (on && !lng) finish_row(P, Lp, p, (long long)q0 + r, hl, A);
+          const float v = acc / (den + 1e-16f);
+          if (tid < P.Hq) Lp.m32[(size_t)p * P.ldh + tid] = v;
+          float f[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = __shfl_sync(0xffffffffu, v, (lane & ~7) + q);
+          if ((lane & 7) == 0 && tid < P.Kh) {
+            uint4 hi, lo;
+            tc::split8(f, hi, lo);
+            *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 0, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = hi;
+            *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 1, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = lo;
+          }
         }
         workers_sync();
-        const int nl = min(S.nlong, kMaxLong);
-        float* part = &S.stage[0][0][0];                       // [16 half-warps][kPartLd]
-        for (int j = 0; j < nl; ++j) {
-          const int r = S.longrow[j];
-          const int p = pos0 + r;
-          const int e0 = D.rowptr[p], e1 = D.rowptr[p + 1];
-          const int hw = 2 * warp + (lane >> 4);
-          GAcc A;
-          gacc_init(A);
-          gather_edges(P, D, Lp, e0 + hw, e1, 4, lstart, hl, wk, ca0, ca1, A);
-          float* mine = part + hw * kPartLd;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(mine + 16 * hl + 4 * q) = A.m[q];
-          if (hl == 0) { mine[256] = A.mx; mine[257] = A.den; }
-          workers_sync();
-          {                                                    // thread = k: merge the 16 partial softmax states
-            float M = -INFINITY;
-#pragma unroll
-            for (int h = 0; h < 16; ++h) M = nanmax(M, part[h * kPartLd + 256]);
-            float den = 0.f, acc = 0.f;
-#pragma unroll
-            for (int h = 0; h < 16; ++h) {
-              const float w = expf(part[h * kPartLd + 256] - M);
-              den = fmaf(part[h * kPartLd + 257], w, den);
-              acc = fmaf(part[h * kPartLd + tid], w, acc);
-            }
-            const float v = acc / (den + 1e-16f);
-            if (tid < P.Hq) Lp.m32[(size_t)p * P.ldh + tid] = v;
-            float f[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = __shfl_sync(0xffffffffu, v, (lane & ~7) + q);
-            if ((lane & 7) == 0 && tid < P.Kh) {
-              uint4 hi, lo;
-              tc::split8(f, hi, lo);
-              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 0, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = hi;
-              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 1, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = lo;
-            }
-          }
-          workers_sync();
-        }
-        if (tid == 0) S.nlong = 0;
       }
-      if (first_layer && !split && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
+      if (nl > 0 && tid == 0) S.nlong = 0;
+      if (nl > 0) workers_sync();
+    };
+    // cells of projection chunk c of this level: TMEM lane = gate * 32 + unit, column = row of the chunk
+    auto cells_chunk = [&](int c) {
+      const int r0 = c * kRC;
+      const int rows = min(kRC, n - r0);
+      const uint32_t set = ct & 1u;
+      const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
+      const int u = u0 + 4 * ug;
+      const bool in_row = u + 4 <= P.Hq;
+      // the aggregate's slice of the first pass. Short levels: every aggregate is visible behind the exchange barrier, the load
+      // flies while the MMAs run. Pipelined levels: other CTAs' rows are only known to be there once the accumulators are (the
+      // copy warp acquired the gather counters before the copies the MMAs consumed) — load behind that wait.
+      float4 mv_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool mv_on = l > 0 && in_row && row < rows && 4 * ug < P.U;
+      if (mv_on && !pipelined) mv_next = ldcg4(Lp.m32 + (size_t)(pos0 + r0 + row) * P.ldh + u);
+      mbar_wait(&S.acc_full[set], (ct >> 1) & 1u);
+      tc::fence_after_sync();
+      if (mv_on && pipelined) mv_next = ldcg4(Lp.m32 + (size_t)(pos0 + r0 + row) * P.ldh + u);
+      if (tr && tid == 0 && c == 0) tr[8] = clock64();
+      const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
+#pragma unroll 1
+      for (int s0 = 0; s0 < rows; s0 += kSub) {
+        if (qd < 3) {
+          float v[32];
+          if (acc_id == 0 || l > 0) {
+            tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(kColAcc + (acc_id ? kColAccH : 0) + s0) + set * (uint32_t)kColSet, v);
+            tc::wait_ld();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;         // level 0: hidden state 0, nothing was projected
+          }
+          float* dst = &S.stage[acc_id][32 * qd + lane][0];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j] = v[j];
+        }
+        workers_sync();
+        const int rr = s0 + row;
+        if (rr < rows && 4 * ug < P.U) {
+          const int p = pos0 + r0 + rr;
+          const float4 mv = mv_next;
+          if (l > 0 && in_row && rr + kSub < rows) mv_next = ldcg4(Lp.m32 + (size_t)(p + kSub) * P.ldh + u);
+          float o[4];
+          const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int uu = 4 * ug + k;
+            const float xr = S.stage[0][uu][row], xz = S.stage[0][32 + uu][row], xn = S.stage[0][64 + uu][row];
+            const float hr = S.stage[1][uu][row], hz = S.stage[1][32 + uu][row], hn = S.stage[1][64 + uu][row];
+            const float rg = fast_sigmoid(xr + hr + S.bias[0][uu]);
+            const float zg = fast_sigmoid(xz + hz + S.bias[1][uu]);
+            const float ng = fast_tanh(xn + S.bias[2][uu] + rg * (hn + S.bias[3][uu]));
+            o[k] = ng + zg * (mm[k] - ng);
+          }
+          if (in_row) *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
+          if (has_next && u < P.Kh) {
+            uint32_t h0, h1, l0, l1;
+            tc::split2(o[0], o[1], h0, l0);
+            tc::split2(o[2], o[3], h1, l1);
+            const long long q = (long long)q0 + r0 + rr;
+            unsigned char* ph = oprow_ptr(Lp.himg, 0, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+            unsigned char* pl = oprow_ptr(Lp.himg, 1, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
+            *reinterpret_cast<uint2*>(ph) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
+          }
+        }
+        if (has_next && s0 + kSub >= rows) asm volatile("fence.proxy.async;" ::: "memory");   // the next layer bulk-copies these rows
+        workers_sync();
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_free[set]);
+      // behind the last pass's closing workers_sync: the whole CTA has stored its slice of the chunk's states
+      if (has_next && tid == 0) st_release_u32(P.flags + (size_t)item * kCS + rank, ct + 1u);
+      ct += 1;
+    };
+
+    if (warp < kCWorkWarps) {
+      if (pipelined) {
+        // ---------------- pipelined level: rounds of 128 rows ----------------
+        const uint32_t ct0 = ct;
+        const int rounds = (n + kHalfWarps - 1) / kHalfWarps;
+        int cells_done = 0;
+#pragma unroll 1
+        for (int t = 0; t < rounds; ++t) {
+          const int r_end = min(n, (t + 1) * kHalfWarps);
+          gather_rows(t * kHalfWarps + ghw, kHalfWarps, r_end);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          workers_sync();
+          if (tid == 0) st_release_u32(mflag + rank, ct0 + (uint32_t)((r_end + kRC - 1) / kRC));
+          if (first_layer && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, min(Tn.y, (t + 1) * kHalfWarps), t * kHalfWarps + ghw, kHalfWarps, hl);
+          const int upto = t == 0 ? 0 : (t * kHalfWarps) / kRC;     // chunks whose rows were gathered a round ago
+          for (; cells_done < upto; ++cells_done) cells_chunk(cells_done);
+        }
+        if (first_layer && Tn.y > rounds * kHalfWarps) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, rounds * kHalfWarps + ghw, kHalfWarps, hl);
+        if (tr && tid == 0) tr[1] = tr[2] = clock64();
+        for (; cells_done < nchunks; ++cells_done) cells_chunk(cells_done);
+      } else {
+        // ---------------- short level: gather, one exchange barrier, cells ----------------
+        // the dependent-load chains of the two jobs would add up in a warp, so warps 0..3 gather and warps 4..7 convert the next
+        // level's input rows at the same time
+        const bool split = first_layer && exchange && n <= kHalfWarps / 2 && Tn.y <= kHalfWarps / 2;
+        const int ghw_s = (((lane >> 4) * (kCWorkWarps / 2) + (warp & 3)) * kCS + rank);      // half-warp index among 64
+        if (split && warp >= kCWorkWarps / 2) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw_s, kHalfWarps / 2, hl);
+        if (exchange) gather_rows(split ? (warp < kCWorkWarps / 2 ? ghw_s : n) : ghw, split ? kHalfWarps / 2 : kHalfWarps, n);
+        if (first_layer && !split && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
+      }
     } else if (warp == kCopyWarp) {
       copy_stages(early);
     } else {
       mma_stages(early);
     }
-    if (tr && tid == 0) tr[1] = clock64();
-    if (exchange) {
-      asm volatile("fence.proxy.async;" ::: "memory");          // operand rows: ordinary stores here, bulk copies (async proxy) there
-      cluster_sync_all();
-    }
-    if (tr && tid == 0) tr[2] = clock64();
-    // ---------------- projection + cell ----------------
-    if (warp == kCopyWarp) {
-      copy_stages(total_stages);
-      if (tr && lane == 0) tr[5] = clock64();
-      ct += (uint32_t)nchunks;
-    } else if (warp == kMmaWarp) {
-      mma_stages(total_stages);
-      if (tr && lane == 0) tr[7] = clock64();
-      ct += (uint32_t)nchunks;
-    } else {
+    if (!pipelined) {
+      if (tr && tid == 0) tr[1] = clock64();
+      if (exchange) {
+        asm volatile("fence.proxy.async;" ::: "memory");          // operand rows: ordinary stores here, bulk copies (async proxy) there
+        cluster_sync_all();
+      }
+      if (tr && tid == 0) tr[2] = clock64();
+      // ---------------- projection + cells ----------------
+      if (warp == kCopyWarp) {
+        copy_stages(total_stages);
+        if (tr && lane == 0) tr[5] = clock64();
+      } else if (warp == kMmaWarp) {
+        mma_stages(total_stages);
+        if (tr && lane == 0) tr[7] = clock64();
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        const int r0 = c * kRC;
-        const int rows = min(kRC, n - r0);
-        // ---- worker warps: epilogue. TMEM lane = gate * 32 + unit, column = row of the chunk.
-        const uint32_t set = ct & 1u;
-        const int row = tid >> 3, ug = tid & 7;                // cell math: 32 rows x 8 groups of 4 units per pass
-        const int u = u0 + 4 * ug;
-        const bool in_row = u + 4 <= P.Hq;
-        float4 mv_next = make_float4(0.f, 0.f, 0.f, 0.f);      // the aggregate's slice of the first pass: in flight while the MMAs run
-        if (l > 0 && in_row && row < rows && 4 * ug < P.U) mv_next = ldcg4(Lp.m32 + (size_t)(pos0 + r0 + row) * P.ldh + u);
-        mbar_wait(&S.acc_full[set], (ct >> 1) & 1u);
-        tc::fence_after_sync();
-        if (tr && tid == 0 && c == 0) tr[8] = clock64();
-        const int qd = warp & 3, acc_id = warp >> 2;           // warps 0..3 read W_ih x, warps 4..7 W_hh m
-#pragma unroll 1
-        for (int s0 = 0; s0 < rows; s0 += kSub) {
-          if (qd < 3) {
-            float v[32];
-            if (acc_id == 0 || l > 0) {
-              tc::ld32(tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(kColAcc + (acc_id ? kColAccH : 0) + s0) + set * (uint32_t)kColSet, v);
-              tc::wait_ld();
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;         // level 0: hidden state 0, nothing was projected
-            }
-            float* dst = &S.stage[acc_id][32 * qd + lane][0];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = v[j];
-          }
-          workers_sync();
-          const int rr = s0 + row;
-          if (rr < rows && 4 * ug < P.U) {
-            const int p = pos0 + r0 + rr;
-            const float4 mv = mv_next;
-            if (l > 0 && in_row && rr + kSub < rows) mv_next = ldcg4(Lp.m32 + (size_t)(p + kSub) * P.ldh + u);
-            float o[4];
-            const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int uu = 4 * ug + k;
-              const float xr = S.stage[0][uu][row], xz = S.stage[0][32 + uu][row], xn = S.stage[0][64 + uu][row];
-              const float hr = S.stage[1][uu][row], hz = S.stage[1][32 + uu][row], hn = S.stage[1][64 + uu][row];
-              const float rg = fast_sigmoid(xr + hr + S.bias[0][uu]);
-              const float zg = fast_sigmoid(xz + hz + S.bias[1][uu]);
-              const float ng = fast_tanh(xn + S.bias[2][uu] + rg * (hn + S.bias[3][uu]));
-              o[k] = ng + zg * (mm[k] - ng);
-            }
-            if (in_row) *reinterpret_cast<float4*>(Lp.Hs + (size_t)p * P.ldh + u) = make_float4(o[0], o[1], o[2], o[3]);
-            if (has_next && u < P.Kh) {
-              uint32_t h0, h1, l0, l1;
-              tc::split2(o[0], o[1], h0, l0);
-              tc::split2(o[2], o[3], h1, l1);
-              const long long q = (long long)q0 + r0 + rr;
-              unsigned char* ph = oprow_ptr(Lp.himg, 0, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
-              unsigned char* pl = oprow_ptr(Lp.himg, 1, P.nckh, P.Q, q, u >> 3) + (u & 4) * 2;
-              *reinterpret_cast<uint2*>(ph) = make_uint2(h0, h1);
-              *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
-            }
-          }
-          if (has_next && s0 + kSub >= rows) asm volatile("fence.proxy.async;" ::: "memory");   // the next layer bulk-copies these rows
-          workers_sync();
-        }
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.tmem_free[set]);
-        // behind the last pass's closing workers_sync: the whole CTA has stored its slice of the chunk's states
-        if (has_next && tid == 0) st_release_u32(P.flags + (size_t)item * kCS + rank, ct + 1u);
-        ct += 1;
+        for (int c = 0; c < nchunks; ++c) cells_chunk(c);
       }
     }
+    if (warp >= kCWorkWarps) ct += (uint32_t)nchunks;
     if (tr && tid == 0) tr[3] = clock64();
     // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
     asm volatile("fence.proxy.async;" ::: "memory");
