@@ -131,6 +131,33 @@ __device__ __forceinline__ uint4 packed_w8(const __half* img, int nck, int col, 
   return __ldg(reinterpret_cast<const uint4*>(img + off));
 }
 
+// 16 bytes into the shared memory of CTA `rank` of the cluster, at the address `saddr` has in this CTA (DSMEM)
+__device__ __forceinline__ void st_cluster_v4(uint32_t saddr, uint32_t rank, const uint4& v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// Levels of <= 32 rows skip global memory for the aggregate operand: the gathering half-warp writes the hi / lo granules of its
+// row straight into the operand slots of ALL CTAs of the cluster (slot = 64-k chunk, 8 KB: groups of 8 rows, hi atom then lo
+// atom — the layout a bulk copy of the operand rows would have produced). `mslot0_s` = shared address of the first such slot.
+__device__ __forceinline__ void store_oprow16_direct(uint32_t mslot0_s, int r, int hl, int K, const float4 (&v)[4]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int gk = 2 * hl + h;
+    if (8 * gk >= K) continue;
+    const float f[8] = {v[2 * h].x, v[2 * h].y, v[2 * h].z, v[2 * h].w, v[2 * h + 1].x, v[2 * h + 1].y, v[2 * h + 1].z, v[2 * h + 1].w};
+    uint4 hi, lo;
+    tc::split8(f, hi, lo);
+    const uint32_t a = mslot0_s + (uint32_t)(gk >> 3) * 8192u + (uint32_t)(r >> 3) * 2048u + (uint32_t)(r & 7) * 128u +
+                       (uint32_t)(((gk & 7) ^ (r & 7)) << 4);
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)kCS; ++c) {
+      st_cluster_v4(a, c, hi);
+      st_cluster_v4(a + 1024u, c, lo);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // gather phase: HALF a warp per node (two nodes per warp in lockstep). Lane hl = lane & 15 owns k = [16 hl, 16 hl + 16) of a
 // row. A node costs its chain of dependent L2 round trips (row pointers -> in-edge list -> predecessor rows), so up to four
@@ -289,12 +316,14 @@ __device__ __forceinline__ void gacc_init(GAcc& A) {
   for (int j = 0; j < 4; ++j) A.m[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 // m_v = (weighted sum) / (denominator + 1e-16) (PyG softmax), stored as an operand row and in fp32
-__device__ __forceinline__ void finish_row(const ClusterP& P, const CLay& Lp, int p, long long q, int hl, GAcc& A) {
+// (direct_s != 0: into the operand slots of every CTA of the cluster instead of the global operand rows; r = row of the level)
+__device__ __forceinline__ void finish_row(const ClusterP& P, const CLay& Lp, int p, long long q, int hl, GAcc& A, uint32_t direct_s, int r) {
   const float inv = 1.f / (A.den + 1e-16f);
   const int k0 = 16 * hl;
 #pragma unroll
   for (int j = 0; j < 4; ++j) { A.m[j].x *= inv; A.m[j].y *= inv; A.m[j].z *= inv; A.m[j].w *= inv; }
-  store_oprow16(Lp.mimg, P.nckh, P.Q, q, hl, P.Kh, A.m);
+  if (direct_s) store_oprow16_direct(direct_s, r, hl, P.Kh, A.m);
+  else store_oprow16(Lp.mimg, P.nckh, P.Q, q, hl, P.Kh, A.m);
   float* mo = Lp.m32 + (size_t)p * P.ldh + k0;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   if (first_layer && L > 0) {
     const int4 T0 = __ldcg(tab);
     if (warp < kCWorkWarps) convert_x_rows(P, D, d, T0.x, T0.z, T0.y, ghw, kHalfWarps, hl);
-    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     cluster_sync_all();
   }
 
@@ -456,6 +485,9 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     const bool pipelined = exchange && n > kCS * kCWorkWarps * 2;               // more rows than half-warps in the cluster (see below)
     unsigned int* mflag = P.flags + (size_t)(kCMaxItems + item) * kCS;          // chunks of aggregates gathered, per CTA of this cluster
     const int ns_gate = pipelined ? nck_in : -1;                                // copy warp: stage k == ns_gate waits for the counters
+    // levels of <= 32 rows: the aggregate operand goes straight into every CTA's operand slots (DSMEM), no copies for it
+    const bool direct = exchange && n <= 32;
+    const uint32_t direct_s = direct ? ring_s + (uint32_t)nck_in * 8192u : 0u;
 
     // The projection of a level is a linear sequence of stages j = chunk * ns + k (k < nck_in: a 64-k chunk of the input
     // operand, then the 64-k chunks of the aggregate operand). The COPY warp starts one bulk copy per stage (hi + lo tile of
@@ -481,6 +513,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
 #pragma unroll 1
       for (; cur.j < j_hi; advance(cur)) {
         const int c = cur.c, k = cur.k, slot = cur.slot;
+        if (direct && k >= nck_in) continue;                   // written by the gathering half-warps of the cluster
         const int r0 = c * kRC;
         const uint32_t bytes = (uint32_t)((min(kRC, n - r0) + 7) >> 3) * 2048u;     // hi + lo atom of every 8-row group
         // MMAs of the stage that used this slot before (this level): committed by the MMA warp, wait for them to finish
@@ -491,14 +524,14 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
           const unsigned int* fl = P.flags + (size_t)(item - P.dirs * P.G) * kCS + (lane & (kCS - 1));
           const unsigned int want = ct + (unsigned int)c + 1u;
           while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= want)) {}
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         if (k == ns_gate) {
           // pipelined level: the aggregate rows of this chunk are there once every CTA of the cluster has counted it
           const unsigned int* fl = mflag + (lane & (kCS - 1));
           const unsigned int want = ct + (unsigned int)c + 1u;
           while (!__all_sync(0xffffffffu, ld_acquire_u32(fl) >= want)) {}
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         if (elect_one()) {
           const bool is_in = k < nck_in;
@@ -517,8 +550,11 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
       for (; cur.j < j_hi; advance(cur)) {
         const int c = cur.c, k = cur.k, slot = cur.slot;
         const uint32_t cc = ct + (uint32_t)c, set = cc & 1u;
-        mbar_wait(&S.full[slot], (full_par >> slot) & 1u);
-        full_par ^= 1u << slot;
+        const bool in_slot = direct && k >= nck_in;            // operand already in the slot (DSMEM), behind the exchange barrier
+        if (!in_slot) {
+          mbar_wait(&S.full[slot], (full_par >> slot) & 1u);
+          full_par ^= 1u << slot;
+        }
         if (k == 0 && cc >= 2) mbar_wait(&S.tmem_free[set], ((cc >> 1) - 1u) & 1u);   // this set's previous chunk has been read
         tc::fence_after_sync();
         const bool is_in = k < nck_in;
@@ -574,7 +610,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
           }
         }
         if (elect_one()) {
-          tc::commit(&S.empty[slot]);
+          if (!in_slot) tc::commit(&S.empty[slot]);
           if (k == ns - 1) tc::commit(&S.acc_full[set]);
         }
         __syncwarp();
@@ -608,7 +644,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         GAcc A;
         gacc_init(A);
         gather_edges(P, D, Lp, e0, e1, 0, lstart, hl, wk, ca0, ca1, A);
-        if (on && !lng) finish_row(P, Lp, p, (long long)q0 + r, hl, A);
+        if (on && !lng) finish_row(P, Lp, p, (long long)q0 + r, hl, A, direct_s, r);
       }
       workers_sync();
       const int nl = min(S.nlong, kMaxLong);
@@ -645,8 +681,15 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
           if ((lane & 7) == 0 && tid < P.Kh) {
             uint4 hi, lo;
             tc::split8(f, hi, lo);
-            *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 0, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = hi;
-            *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 1, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = lo;
+            if (direct_s) {
+              const int gk = tid >> 3;
+              const uint32_t a = direct_s + (uint32_t)(gk >> 3) * 8192u + (uint32_t)(r >> 3) * 2048u + (uint32_t)(r & 7) * 128u +
+                                 (uint32_t)(((gk & 7) ^ (r & 7)) << 4);
+              for (uint32_t c = 0; c < (uint32_t)kCS; ++c) { st_cluster_v4(a, c, hi); st_cluster_v4(a + 1024u, c, lo); }
+            } else {
+              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 0, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = hi;
+              *reinterpret_cast<uint4*>(oprow_ptr(Lp.mimg, 1, P.nckh, P.Q, (long long)q0 + r, tid >> 3)) = lo;
+            }
           }
         }
         workers_sync();
@@ -718,7 +761,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
             *reinterpret_cast<uint2*>(pl) = make_uint2(l0, l1);
           }
         }
-        if (has_next && s0 + kSub >= rows) asm volatile("fence.proxy.async;" ::: "memory");   // the next layer bulk-copies these rows
+        if (has_next && s0 + kSub >= rows) asm volatile("fence.proxy.async.global;" ::: "memory");   // the next layer bulk-copies these rows
         workers_sync();
       }
       tc::fence_before_sync();
@@ -739,7 +782,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         for (int t = 0; t < rounds; ++t) {
           const int r_end = min(n, (t + 1) * kHalfWarps);
           gather_rows(t * kHalfWarps + ghw, kHalfWarps, r_end);
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
           workers_sync();
           if (tid == 0) st_release_u32(mflag + rank, ct0 + (uint32_t)((r_end + kRC - 1) / kRC));
           if (first_layer && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, min(Tn.y, (t + 1) * kHalfWarps), t * kHalfWarps + ghw, kHalfWarps, hl);
@@ -767,7 +810,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     if (!pipelined) {
       if (tr && tid == 0) tr[1] = clock64();
       if (exchange) {
-        asm volatile("fence.proxy.async;" ::: "memory");          // operand rows: ordinary stores here, bulk copies (async proxy) there
+        if (direct) asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); else asm volatile("fence.proxy.async.global;" ::: "memory");          // operand rows: ordinary stores here, bulk copies (async proxy) there
         cluster_sync_all();
       }
       if (tr && tid == 0) tr[2] = clock64();
@@ -786,7 +829,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     if (warp >= kCWorkWarps) ct += (uint32_t)nchunks;
     if (tr && tid == 0) tr[3] = clock64();
     // the states of this level: read by this cluster's next gather phase (other CTAs), by the next layer's bulk copies
-    asm volatile("fence.proxy.async;" ::: "memory");
+    if (first_layer) asm volatile("fence.proxy.async.global;" ::: "memory");   // next level's input rows (bulk-copied); the states are read by plain loads
     cluster_sync_all();
     if (tr && tid == 0) tr[4] = clock64();
   }
