@@ -6,7 +6,7 @@ Same constructor signature, same parameter names/shapes (checkpoints of the refe
 `edge_index int64[2,E]`, `edge_attr fp32[E,2]`, `batch int64[N]`, `_bi_layer_idx0/1`, `_bi_layer_index0/1`
 on the CUDA device; returns a list of `max_seq_len` tensors `[B, num_vocab]` (or `[B, num_class]`).
 
-Scope: the default aggregator `agg="attn_h"` with GRU cells (`recurr=1`), uni/bidirectional,
+Scope: the aggregators `agg="attn_h"` (default) and `"self_attn_h"` with GRU cells (`recurr=1`), uni/bidirectional,
 `out_wx`, `out_pool_all`, `out_pool` in {max, mean, add, attn}. Other aggregators / `agg_x` / `recurr=0` raise
 NotImplementedError at construction (§8f row 4), they never fall back to eager torch.
 Training: with autograd enabled the forward runs through `dagnn_b200.autograd` (EmbedFn, SweepReadoutFn, LinearFn), whose
@@ -22,6 +22,7 @@ from . import autograd as ag
 from . import runtime as rt
 
 NA_ATTN_H = "attn_h"
+NA_SELF_ATTN_H = "self_attn_h"
 P_MAX, P_MEAN, P_ADD, P_ATTN = "max", "mean", "add", "attn"
 
 
@@ -57,6 +58,21 @@ class AttnConv(nn.Module):
         self.attn_lin = nn.Linear(attn_q_dim + attn_dim, 1)
 
 
+class SelfAttnConv(nn.Module):
+    """Parameter container with the names of the reference's SelfAttnConv (dagnn.py:279-313): the same additive attention
+    without a query part — score = attn_lin(h_j + edge embedding). In the level kernel this is AttnConv with Dq = 0."""
+
+    def __init__(self, emb_dim, attn_dim=0, num_relations=1, reverse=False):
+        super().__init__()
+        assert emb_dim > 0
+        attn_dim = attn_dim if attn_dim > 0 else emb_dim
+        self.reverse = reverse
+        self.wea = num_relations > 1
+        if self.wea:
+            self.edge_encoder = nn.Linear(num_relations, attn_dim)
+        self.attn_lin = nn.Linear(attn_dim, 1)
+
+
 class _PackedCacheMixin(object):
     """Drops the packed-parameter cache whenever parameters may have been rewritten behind autograd's version counters."""
 
@@ -86,8 +102,8 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         self.max_seq_len = max_seq_len
         if agg_x and hidden_dim < emb_dim:
             raise ValueError('Hidden dimension too small for input.')     # dagnn.py:27-28
-        if agg != NA_ATTN_H or agg_x or not recurr:
-            raise NotImplementedError("dagnn_b200 covers agg='attn_h', agg_x=False, recurr=1 (SURVEY.md §8f row 4); "
+        if agg not in (NA_ATTN_H, NA_SELF_ATTN_H) or agg_x or not recurr:
+            raise NotImplementedError("dagnn_b200 covers agg='attn_h' / 'self_attn_h', agg_x=False, recurr=1 (SURVEY.md §8f row 4); "
                                       "got agg=%r agg_x=%r recurr=%r" % (agg, agg_x, recurr))
         if out_pool not in (P_MAX, P_MEAN, P_ADD, P_ATTN):
             raise ValueError("out_pool=%r (max / mean / add / attn)" % (out_pool,))
@@ -112,10 +128,14 @@ class DAGNN(_PackedCacheMixin, nn.Module):
         if num_rels not in (1, 2):
             raise NotImplementedError("edge_attr must have 2 columns (utils2.py:45,68)")
         # both aggregator lists exist even when unidirectional, like the reference (dagnn.py:64-67)
-        self.node_aggr_0 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
-                                                   attn_dim=hidden_dim) for l in range(num_layers)])
-        self.node_aggr_1 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
-                                                   attn_dim=hidden_dim, reverse=True) for l in range(num_layers)])
+        if agg == NA_SELF_ATTN_H:          # dagnn.py:56-61
+            self.node_aggr_0 = nn.ModuleList([SelfAttnConv(hidden_dim, num_relations=num_rels) for _ in range(num_layers)])
+            self.node_aggr_1 = nn.ModuleList([SelfAttnConv(hidden_dim, num_relations=num_rels, reverse=True) for _ in range(num_layers)])
+        else:                              # dagnn.py:62-67
+            self.node_aggr_0 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
+                                                       attn_dim=hidden_dim) for l in range(num_layers)])
+            self.node_aggr_1 = nn.ModuleList([AttnConv(emb_dim if l == 0 else hidden_dim, hidden_dim, num_relations=num_rels,
+                                                       attn_dim=hidden_dim, reverse=True) for l in range(num_layers)])
         for i in self.dirs:
             setattr(self, "cells_{}".format(i), nn.ModuleList(
                 [nn.GRUCell(emb_dim if l == 0 else hidden_dim, hidden_dim) for l in range(num_layers)]))

@@ -124,7 +124,10 @@ def attn_conv(h, edge_index, h_attn_q, h_attn, attn_w, attn_b, edge_attr=None, e
     key = h_attn.index_select(0, nbr)
     if edge_w is not None:
         key = key + F.linear(edge_attr, edge_w, edge_b)
-    a = F.linear(torch.cat([h_attn_q.index_select(0, tgt), key], dim=-1), attn_w, attn_b)
+    if h_attn_q is None:      # SelfAttnConv, dagnn.py:296-310: no query part
+        a = F.linear(key, attn_w, attn_b)
+    else:
+        a = F.linear(torch.cat([h_attn_q.index_select(0, tgt), key], dim=-1), attn_w, attn_b)
     a = segment_softmax(a, tgt, h.shape[0])
     msg = h.index_select(0, nbr) * a
     out = h.new_zeros(h.shape[0], h.shape[1])
@@ -134,7 +137,7 @@ def attn_conv(h, edge_index, h_attn_q, h_attn, attn_w, attn_b, edge_attr=None, e
 # ----------------------------------------------------------------------------- the level sweep
 def level_sweep(x, edge_index, bi_layer_index, p: Dict[str, torch.Tensor], num_layers: int, dirs: List[int],
                 hidden_dim: int, edge_attr=None, vid_nodes: int = 0, trace: Optional[dict] = None,
-                cell_prefix="cells_{}.{}."):
+                cell_prefix="cells_{}.{}.", self_attn: bool = False):
     """ogbg-code/model/dagnn.py:141-182 / dvae/dagnn.py:106-145 / dvae/dagnn_bn.py:105-136.
 
     Returns H[d][i] (float32 [N, hidden]) for every direction/layer. `vid_nodes` > 0 appends the D-VAE
@@ -169,7 +172,7 @@ def level_sweep(x, edge_index, bi_layer_index, p: Dict[str, torch.Tensor], num_l
                         keys = H[d][i]
                         q = H[d][i - 1] if i > 0 else x
                     ap = "node_aggr_{}.{}.".format(d, i)
-                    ps_h = attn_conv(H[d][i], lp_edge_index, q, keys, p[ap + "attn_lin.weight"],
+                    ps_h = attn_conv(H[d][i], lp_edge_index, None if self_attn else q, keys, p[ap + "attn_lin.weight"],
                                      p[ap + "attn_lin.bias"],
                                      edge_attr[le_idx] if has_ea else None,
                                      p.get(ap + "edge_encoder.weight") if has_ea else None,
@@ -221,7 +224,7 @@ def ogb_readout(G, X, H, num_layers, bidirectional=True, out_wx=False, out_pool_
 
 def ogb_forward(p: Dict[str, torch.Tensor], G, num_layers=2, bidirectional=True, out_wx=False,
                 out_pool_all=False, out_pool="max", max_seq_len=5, num_class=0, w_edge_attr=True,
-                heads=True, trace: Optional[dict] = None):
+                heads=True, trace: Optional[dict] = None, agg="attn_h"):
     """ogbg-code/model/dagnn.py:128-215 with agg='attn_h', recurr=1, encoder=ASTNodeEncoder.
     Returns (pred_list | logits, readout [B, out_hidden], H)."""
     dirs = [0, 1] if bidirectional else [0]
@@ -230,7 +233,7 @@ def ogb_forward(p: Dict[str, torch.Tensor], G, num_layers=2, bidirectional=True,
     X = ast_node_encoder(G.x, G.node_depth.view(-1), p)
     hidden = p["cells_0.0.weight_hh"].shape[1]
     H = level_sweep(X, G.edge_index, bi, p, num_layers, dirs, hidden,
-                    edge_attr=G.edge_attr if w_edge_attr else None, trace=trace)
+                    edge_attr=G.edge_attr if w_edge_attr else None, trace=trace, self_attn=(agg == "self_attn_h"))
     out = ogb_readout(G, X, H, num_layers, bidirectional, out_wx, out_pool_all, out_pool)
     if not heads:
         return None, out, H

@@ -48,6 +48,9 @@ OGB_CASES = [
     dict(name="ogb_code2_h72_l3_mean_all", gen=("code2", 4, 20265), emb=48, hid=72, layers=3, bidir=True, out_wx=False,
          pool_all=1, pool="mean", wea=True, num_class=0, wseed=14),
     # out_pool="attn": Linear(d, 1) scores softmaxed over a size-1 dimension = add-pool (dagnn.py:114-117)
+    # agg="self_attn_h" (SelfAttnConv, dagnn.py:279-313)
+    dict(name="ogb_code2_self_attn", gen=("code2", 4, 20267), emb=40, hid=56, layers=2, bidir=True, out_wx=False,
+         pool_all=0, pool="max", wea=True, num_class=0, wseed=19, agg="self_attn_h"),
     dict(name="ogb_rand_attn_pool", gen=("rand", 5, 23), emb=16, hid=24, layers=2, bidir=True, out_wx=False,
          pool_all=0, pool="attn", wea=True, num_class=0, wseed=16),
 ]
@@ -114,7 +117,7 @@ def gen_ogb(case):
     enc = utl.ASTNodeEncoder(case["emb"], D.CODE2_NUM_NODETYPES, D.CODE2_NUM_NODEATTRS, D.CODE2_MAX_DEPTH)
     m = dag.DAGNN(50, 5, case["emb"], case["hid"], None, encoder=enc, w_edge_attr=case["wea"],
                   num_layers=case["layers"], bidirectional=case["bidir"], out_wx=case["out_wx"],
-                  out_pool_all=case["pool_all"], out_pool=case["pool"], num_class=case["num_class"])
+                  out_pool_all=case["pool_all"], out_pool=case["pool"], num_class=case["num_class"], agg=case.get("agg", "attn_h"))
     D.deterministic_init_(m, case["wseed"])
     m.eval()
     G = Batch(batch=B.batch.clone(), x=B.x.clone(), edge_index=B.edge_index.clone(),

@@ -34,7 +34,7 @@ def ogb_module_from_meta(meta, device=None, cls=None, enc_cls=None):
     enc = enc_cls(meta["emb"], D.CODE2_NUM_NODETYPES, D.CODE2_NUM_NODEATTRS, D.CODE2_MAX_DEPTH)
     m = cls(50, 5, meta["emb"], meta["hid"], None, encoder=enc, w_edge_attr=meta["wea"], num_layers=meta["layers"],
             bidirectional=meta["bidir"], out_wx=meta["out_wx"], out_pool_all=meta["pool_all"], out_pool=meta["pool"],
-            num_class=meta["num_class"])
+            num_class=meta["num_class"], agg=meta.get("agg", "attn_h"))
     D.deterministic_init_(m, meta["wseed"])
     m.eval()
     return m.to(device) if device is not None else m
@@ -53,6 +53,6 @@ def dvae_module_from_meta(meta, device=None):
 
 
 OGB_GOLDEN = ["ogb_rand_bidir", "ogb_rand_unidir3", "ogb_rand_noattr_mean", "ogb_rand_wx_add_cls", "ogb_code2_small",
-              "ogb_code2_h300x5", "ogb_rand_h30_l1_add", "ogb_code2_h72_l3_mean_all", "ogb_rand_attn_pool"]
+              "ogb_code2_h300x5", "ogb_rand_h30_l1_add", "ogb_code2_h72_l3_mean_all", "ogb_rand_attn_pool", "ogb_code2_self_attn"]
 DVAE_GOLDEN = ["na_real_hs64", "na_real_hs501", "na_real_bidir_hs48", "bn_real_hs64", "bn_real_hs501",
                "bn_real_unidir_hs40", "na_real_unidir_l3_hs36", "bn_real_pool_all_mean_hs40", "na_real_pool_all_max_hs32"]

@@ -77,6 +77,7 @@ OGB_CASES = [
     (4, 14, 64, 64, 2, True, "code2", dict(out_wx=True, out_pool="add")),
     (6, 15, 20, 28, 2, True, "rand", dict(w_edge_attr=False, out_pool_all=True, out_pool="mean")),
     (3, 16, 256, 256, 2, True, "code2", {}),
+    (5, 17, 32, 48, 2, True, "code2", dict(agg="self_attn_h")),
 ]
 
 
@@ -94,7 +95,7 @@ def test_ogb_gradients_match_oracle_autograd(ng, seed, emb, hid, layers, bidir, 
     # ---- reference: autograd through the CPU oracle
     p = {k: v.clone().requires_grad_(True) for k, v in state_dict_cpu(m).items()}
     preds, _, _ = O.ogb_forward(p, B, num_layers=layers, bidirectional=bidir, out_wx=args["out_wx"], out_pool_all=args["out_pool_all"],
-                                out_pool=args.get("out_pool", "max"), w_edge_attr=args.get("w_edge_attr", True))
+                                out_pool=args.get("out_pool", "max"), w_edge_attr=args.get("w_edge_attr", True), agg=args.get("agg", "attn_h"))
     g = torch.Generator().manual_seed(seed)
     ws = [torch.randn(preds[0].shape, generator=g) for _ in preds]
     sum((pr * w).sum() for pr, w in zip(preds, ws)).backward()

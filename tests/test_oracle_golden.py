@@ -20,7 +20,7 @@ def test_ogb_oracle_matches_reference_fixture(name):
     with torch.no_grad():
         pred, out, H = O.ogb_forward(p, B, num_layers=meta["layers"], bidirectional=meta["bidir"], out_wx=meta["out_wx"],
                                      out_pool_all=bool(meta["pool_all"]), out_pool=meta["pool"], max_seq_len=5,
-                                     num_class=meta["num_class"], w_edge_attr=meta["wea"], trace=trace)
+                                     num_class=meta["num_class"], w_edge_attr=meta["wea"], trace=trace, agg=meta.get("agg", "attn_h"))
     np.testing.assert_allclose(out.numpy(), z["readout"], atol=TOL, rtol=0)
     pred = pred if meta["num_class"] > 0 else torch.stack(pred)
     np.testing.assert_allclose(pred.numpy(), z["pred"], atol=TOL, rtol=0)
