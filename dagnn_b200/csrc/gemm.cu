@@ -6,9 +6,11 @@
 // by the small dense layers of the modules (heads, out_linear / hg_unify, fc1 / fc2): replaces the cuBLAS calls behind
 // nn.Linear / nn.GRUCell's backward (ogbg-code/model/dagnn.py:181,209-215; dvae/dagnn.py:156,161,183).
 //
-// One CTA per 128 x 128 tile of C, 8 warps: all of them convert the fp32 operand chunks (64 k) into fp16 hi / lo halves in
-// K-major SWIZZLE_128B tiles (two stages, so the conversion of chunk c + 1 overlaps the MMAs of chunk c), one elected lane of
-// warp 0 issues tcgen05.mma kind::f16 (M = 128, N = 128: hi*hi + lo*hi + hi*lo) into a TMEM accumulator, all warps drain it.
+// One CTA per 128 x 128 tile of C (x one slice of K), 8 warps: all of them convert the fp32 operand chunks (64 k) into fp16
+// hi / lo halves in K-major SWIZZLE_128B tiles, one elected lane of warp 0 issues tcgen05.mma kind::f16 (M = 128, N = 128:
+// hi*hi + lo*hi + hi*lo) into a TMEM accumulator. One 64 KB stage per CTA: up to three CTAs share an SM and overlap each
+// other's conversion, MMAs and epilogue. Epilogue: TMEM -> registers -> shared memory (rotated columns, conflict-free) ->
+// row-contiguous global stores.
 #include "common.cuh"
 #include "sync.cuh"
 #include "tc.cuh"
@@ -17,7 +19,7 @@ namespace dagnn {
 
 constexpr int kGT = 128;                                   // tile rows (M) and columns (N)
 constexpr int kGStage = 4 * kGT * tc::ROW_BYTES;           // A hi, A lo, B hi, B lo tiles of one 64-k chunk = 64 KB
-constexpr size_t kGSmem = 1024 + 2 * (size_t)kGStage + 64;
+constexpr size_t kGSmem = 1024 + (size_t)kGStage + 64;     // ONE stage: three CTAs fit an SM (3 x 128 TMEM columns) and overlap each other
 
 struct GemmP {
   const float* A; const float* B; float* C; const float* bias;
@@ -63,10 +65,10 @@ __device__ __forceinline__ void stage_operand(const float* __restrict__ X, long 
   }
 }
 
-__global__ void __launch_bounds__(256, 1) k_gemm_f16x3(const __grid_constant__ GemmP P) {
+__global__ void __launch_bounds__(256, 3) k_gemm_f16x3(const __grid_constant__ GemmP P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * (size_t)kGStage);       // [2] stage free (its MMAs are done)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)kGStage);           // [0]: the MMAs issued so far are done
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (warp == 0) tc::tmem_alloc(slot, 128);
@@ -83,10 +85,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16x3(const __grid_constant__ G
   const int c_begin = blockIdx.z * P.chunks_per;
   const int nchunks = min(P.chunks_per, all_chunks - c_begin);           // >= 1 by construction of the grid
   const uint32_t idesc = tc::instr_desc_f16(128, kGT);
+  unsigned char* st = base;
   for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    unsigned char* st = base + (size_t)s * kGStage;
-    if (c >= 2) mbar_wait(&bar[s], ((c >> 1) - 1) & 1u);       // the MMAs that read this stage two chunks ago are done
+    if (c >= 1) mbar_wait(&bar[0], (uint32_t)(c - 1) & 1u);    // the MMAs that read the stage are done
     const int k0 = (c_begin + c) * 64;
     stage_operand(P.A, P.lda, P.M, P.K, m0, k0, P.a_kmajor, P.a_vec, st, st + kGT * tc::ROW_BYTES, tid);
     stage_operand(P.B, P.ldb, P.N, P.K, n0, k0, P.b_kmajor, P.b_vec, st + 2 * kGT * tc::ROW_BYTES, st + 3 * kGT * tc::ROW_BYTES, tid);
@@ -101,33 +102,40 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16x3(const __grid_constant__ G
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) tc::mma3_f16(tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, fresh && ks == 0);
-        tc::commit(&bar[s]);
-        if (c + 1 == nchunks) tc::commit(&bar[2]);
+        tc::commit(&bar[0]);
       }
       __syncwarp();
     }
   }
-  mbar_wait(&bar[2], 0u);
+  mbar_wait(&bar[0], (uint32_t)(nchunks - 1) & 1u);
   tc::fence_after_sync();
-  // epilogue: TMEM lane = row of the tile; warps w and w + 4 split the columns
+  // epilogue: TMEM lane = row of the tile (warps w and w + 4 split the columns) -> the stage memory as a [128][128] fp32 tile
+  // with the columns of row r rotated by r (a warp storing one column of 32 rows, and a warp reading one row, both touch 32
+  // different banks) -> every warp stores whole rows: 128 contiguous floats per row
+  float* tile = reinterpret_cast<float*>(st);
   {
     const int q = warp & 3, half = warp >> 2;
-    const int row = m0 + 32 * q + lane;
+    const int r = 32 * q + lane;
     for (int cb = half * 8; cb < half * 8 + 8; ++cb) {
       float v[8];
       tc::ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 8), v);
       tc::wait_ld();
-      if (row < P.M) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = n0 + cb * 8 + j;
-          if (col < P.N) {
-            float* o = P.C + (size_t)row * P.ldc + col;
-            float r = v[j] + ((P.bias && blockIdx.z == 0) ? __ldg(P.bias + col) : 0.f);
-            if (P.ksplit > 1) atomicAdd(o, r);                 // C was zeroed by the launcher unless it accumulates anyway
-            else { if (P.beta) r += *o; *o = r; }
-          }
-        }
+      for (int j = 0; j < 8; ++j) tile[r * kGT + ((cb * 8 + j + r) & (kGT - 1))] = v[j];
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < kGT; r += 8) {
+    const int row = m0 + r;
+    if (row >= P.M) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = lane + 32 * j, col = n0 + cl;
+      if (col < P.N) {
+        float* o = P.C + (size_t)row * P.ldc + col;
+        float x = tile[r * kGT + ((cl + r) & (kGT - 1))] + ((P.bias && blockIdx.z == 0) ? __ldg(P.bias + col) : 0.f);
+        if (P.ksplit > 1) atomicAdd(o, x);                     // C was zeroed by the launcher unless it accumulates anyway
+        else { if (P.beta) x += *o; *o = x; }
       }
     }
   }

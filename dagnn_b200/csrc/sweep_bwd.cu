@@ -196,6 +196,132 @@ __global__ void __launch_bounds__(256) k_bwd_attn(const AttnP A, const float* __
     if (dwk_s[u] != 0.f) atomicAdd(dwk + u, dwk_s[u]);
 }
 
+// Short levels (the tail of the level chain: a handful of rows each): the three steps of a level in ONE launch, one CTA per
+// row — gate gradients, dm = z dh + dGh W_hh as a matrix-vector product against W_hh streamed from L2 (coalesced: thread =
+// hidden unit), softmax / score backward over the row's in-edges by the CTA's 8 warps. dGi / dGh rows still go to global
+// memory (the weight-gradient GEMMs read them at the end).
+constexpr int kFusedMaxH = 768;                    // 12 H + 16 floats of shared memory per CTA stay under the 48 KB default
+__global__ void __launch_bounds__(256) k_bwd_level_fused(const AttnP A, const float* __restrict__ G1, const float* __restrict__ G2, long long ldg,
+                                                         const float* __restrict__ M, const float* __restrict__ alpha, const float* __restrict__ W_hh,
+                                                         float* __restrict__ dH, float* __restrict__ dGi, float* __restrict__ dGh, int a,
+                                                         float* __restrict__ dwk, float* __restrict__ dca, float* __restrict__ dvid) {
+  extern __shared__ float sm[];                    // [3H] dGh row | [H] dm row | [8] partial S | [1] S | pad | [8][H] GEMV partials
+  const int H = A.H;
+  float* sgh = sm;
+  float* sdm = sm + 3 * H;
+  float* spart = sdm + H;
+  const int p = a + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* g1 = G1 + (size_t)p * ldg;
+  for (int u = tid; u < H; u += 256) {
+    const float r = g1[u], z = g1[H + u], n = g1[2 * H + u], hn = G2[(size_t)p * ldg + 2 * H + u];
+    const float m = M[(size_t)p * A.ldh + u], dh = dH[(size_t)p * A.ldh + u];
+    const float dn = dh * (1.f - z), dz = dh * (m - n);
+    const float dpn = dn * (1.f - n * n);
+    const float dar = dpn * hn * r * (1.f - r), daz = dz * z * (1.f - z);
+    float* gi = dGi + (size_t)p * ldg;
+    float* gh = dGh + (size_t)p * ldg;
+    gi[u] = dar; gi[H + u] = daz; gi[2 * H + u] = dpn;
+    gh[u] = dar; gh[H + u] = daz; gh[2 * H + u] = dpn * r;
+    sgh[u] = dar; sgh[H + u] = daz; sgh[2 * H + u] = dpn * r;
+    sdm[u] = dh * z;
+  }
+  __syncthreads();
+  // dm[u] += sum_k dGh[k] W_hh[k, u]: warp w takes the rows k = w, w + 8, ... of W_hh, a lane 4 consecutive units per 128-unit
+  // slab (coalesced 16-byte loads), 8 rows in flight per lane; the 8 partial rows are summed through shared memory
+  float* spw = sm + 4 * H + 16;                    // [8][H] partial sums of the warps
+  for (int ub = 0; ub < H; ub += 128) {
+    const int u = ub + 4 * lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u + 4 <= H && (H & 3) == 0) {
+      int k = warp;
+      for (; k + 120 < 3 * H; k += 128) {              // 16 rows of W_hh in flight per lane: the product is bound by L2 latency
+        float4 wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(W_hh + (size_t)(k + 8 * j) * H + u));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = sgh[k + 8 * j];
+          acc.x = fmaf(g, wv[j].x, acc.x); acc.y = fmaf(g, wv[j].y, acc.y); acc.z = fmaf(g, wv[j].z, acc.z); acc.w = fmaf(g, wv[j].w, acc.w);
+        }
+      }
+      for (; k < 3 * H; k += 8) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(W_hh + (size_t)k * H + u));
+        const float g = sgh[k];
+        acc.x = fmaf(g, wv.x, acc.x); acc.y = fmaf(g, wv.y, acc.y); acc.z = fmaf(g, wv.z, acc.z); acc.w = fmaf(g, wv.w, acc.w);
+      }
+    } else {
+      for (int k = warp; k < 3 * H; k += 8) {
+        const float g = sgh[k];
+        if (u < H) acc.x = fmaf(g, __ldg(W_hh + (size_t)k * H + u), acc.x);
+        if (u + 1 < H) acc.y = fmaf(g, __ldg(W_hh + (size_t)k * H + u + 1), acc.y);
+        if (u + 2 < H) acc.z = fmaf(g, __ldg(W_hh + (size_t)k * H + u + 2), acc.z);
+        if (u + 3 < H) acc.w = fmaf(g, __ldg(W_hh + (size_t)k * H + u + 3), acc.w);
+      }
+    }
+    if (u < H) spw[warp * H + u] = acc.x;
+    if (u + 1 < H) spw[warp * H + u + 1] = acc.y;
+    if (u + 2 < H) spw[warp * H + u + 2] = acc.z;
+    if (u + 3 < H) spw[warp * H + u + 3] = acc.w;
+  }
+  __syncthreads();
+  for (int u = tid; u < H; u += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += spw[w8 * H + u];
+    sdm[u] += t;
+  }
+  __syncthreads();
+  // ---- attention backward: edges of the row dealt to the 8 warps
+  const int e0 = A.rowptr[p], e1 = A.rowptr[p + 1];
+  const int lstart = a;
+  const float* wk = A.attn_w + A.Dq;
+  float Sp = 0.f;
+  for (int e = e0 + warp; e < e1; e += 8) {
+    const int sp = A.col[e];
+    if (sp < lstart) {
+      float dt = 0.f;
+      const float* h = A.Hs + (size_t)sp * A.ldh;
+      for (int u = lane; u < H; u += 32) dt = fmaf(sdm[u], h[u], dt);
+      Sp = fmaf(alpha[e], warp_sum(dt), Sp);
+    }
+  }
+  if (lane == 0) spart[warp] = Sp;
+  __syncthreads();
+  if (tid == 0) {
+    float S = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) S += spart[w8];
+    spart[8] = S;
+  }
+  __syncthreads();
+  const float S = spart[8];
+  float c0 = 0.f, c1 = 0.f;
+  for (int e = e0 + warp; e < e1; e += 8) {
+    const int sp = A.col[e];
+    const bool valid = sp < lstart;
+    const float al = alpha[e];
+    float da = 0.f;
+    const float* h = A.Hs + (size_t)sp * A.ldh;
+    if (valid) {
+      float dt = 0.f;
+      for (int u = lane; u < H; u += 32) dt = fmaf(sdm[u], h[u], dt);
+      da = warp_sum(dt);
+    }
+    const float ds = al * (da - S);
+    if (valid) {
+      float* dh = dH + (size_t)sp * A.ldh;
+      for (int u = lane; u < H; u += 32) {
+        atomicAdd(dh + u, fmaf(al, sdm[u], ds * __ldg(wk + u)));
+        atomicAdd(dwk + u, ds * h[u]);
+      }
+    }
+    if (lane == 0) {
+      if (A.eattr) { c0 = fmaf(ds, A.eattr[2 * (size_t)e], c0); c1 = fmaf(ds, A.eattr[2 * (size_t)e + 1], c1); }
+      if (A.nvid > 0) atomicAdd(dvid + (A.perm[sp] % A.nvid), ds);
+    }
+  }
+  if (lane == 0 && A.eattr && (c0 != 0.f || c1 != 0.f)) { atomicAdd(dca, c0); atomicAdd(dca + 1, c1); }
+}
+
 // dst[perm[p], :] += src[p, :]   (position order -> node order, one writer per element)
 __global__ void __launch_bounds__(256) k_scatter_rows_add(const int* __restrict__ perm, const float* __restrict__ src, long long lds,
                                                           float* __restrict__ dst, long long ldd, int N, int W) {
@@ -452,6 +578,12 @@ extern "C" int dagnn_sweep_backward_f32(const DagnnSweepBwdArgs* A, void* stream
       for (int l = L - 1; l >= 0; --l) {
         const int a = lo[l], b = lo[l + 1];
         if (b <= a) continue;
+        if (l > 0 && b - a <= 148 && H <= kFusedMaxH && S->E > 0) {             // the tail of the level chain: one launch per level
+          k_bwd_level_fused<<<b - a, 256, (size_t)(12 * H + 16) * sizeof(float), st>>>(ap, w.G1, w.G2, ldg, w.M, w.alpha, pr.weight_hh, dH, w.dGi,
+                                                                                       w.dGh, a, dwk, dca, dvid);
+          if (int rc = check_launch("k_bwd_level_fused")) return rc;
+          continue;
+        }
         k_bwd_cell<<<grid_for((long long)(b - a) * H, 256), 256, 0, st>>>(w.G1, w.G2, ldg, w.M, dH, ldh, w.dGi, w.dGh, w.dM, a, b, H);
         if (int rc = check_launch("k_bwd_cell")) return rc;
         if (l == 0) break;
