@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdagnn_sm100.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "sweep_cluster.cu", "sweep_bwd.cu", "gemm.cu", "tc_selftest.cu"]
+SOURCES = ["abi.cu", "schedule.cu", "levels.cu", "embed_readout.cu", "pack.cu", "sweep.cu", "sweep_cluster.cu", "sweep_bwd.cu", "gemm.cu", "rows.cu", "tc_selftest.cu"]
 HEADERS = ["common.cuh", "sync.cuh", "tc.cuh"]
 
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 vp = C.c_void_p
 
@@ -112,6 +112,8 @@ EXPORTS = {
     "dagnn_readout_backward_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.POINTER(vp), C.c_int32, C.c_int32,
                                              vp, vp, C.c_int64, vp]),
     "dagnn_embed_backward_f32": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, vp, vp, vp, vp]),
+    "dagnn_dvae_rows_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dagnn_dvae_rows_build": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_size_t, vp]),
     "dagnn_readout_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.POINTER(DagnnReadoutBlock), C.c_int32, C.c_int32, vp,
                                     C.c_int64, vp]),
     "dagnn_states_to_node_order_f32": (C.c_int, [C.POINTER(DagnnSchedule), C.c_int32, vp, C.c_int64, C.c_int32, vp,

@@ -109,18 +109,26 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ Readout
     unsigned m = __ballot_sync(0xffffffffu, sel);
     cnt += __popc(m);
     while (m) {
-      const int j0 = __ffs(m) - 1;
-      m &= m - 1;
-      const long long r = __shfl_sync(0xffffffffu, row, j0);
-      const float* srow = b.src + (size_t)r * b.ld + c0;
+      // four selected rows per round, their loads in flight together (the pooled value depends on all of them, a row at a
+      // time is a chain of L2 round trips)
+      float h[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane + 32 * j;
-        if (c0 + c < b.width) {
-          const float h = __ldcg(srow + c);
-          acc[j] = is_max ? ((h > acc[j] || h != h) ? h : acc[j]) : acc[j] + h;     // max keeps a NaN (fmaxf would drop it)
+      for (int t = 0; t < 4; ++t) {
+        const bool on = m != 0u;
+        const int j0 = on ? __ffs(m) - 1 : 0;
+        m &= m - 1;                                     // (0 stays 0)
+        const long long r = __shfl_sync(0xffffffffu, row, j0);
+        const float* srow = b.src + (size_t)r * b.ld + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = lane + 32 * j;
+          h[t][j] = (on && c0 + c < b.width) ? __ldcg(srow + c) : (is_max ? -INFINITY : 0.f);
         }
       }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = is_max ? ((h[t][j] > acc[j] || h[t][j] != h[t][j]) ? h[t][j] : acc[j]) : acc[j] + h[t][j];
     }
   }
 #pragma unroll

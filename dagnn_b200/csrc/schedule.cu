@@ -13,11 +13,12 @@
 
 namespace dagnn {
 
-constexpr int kChunk = 512;
+constexpr int kChunkBig = 512;        // entries of the level arrays per warp: 512 for big batches (a smaller count table),
+constexpr int kChunkSmall = 128;      // 128 below 64 k nodes (4 x the blocks: the two counting-sort passes are latency-bound)
 constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(32) k_sched_count(const int64_t* __restrict__ lvl0, const int64_t* __restrict__ lvl1,
-                                                    int N, int nchunks, int max_levels, int* __restrict__ cnt0,
+                                                    int N, int nchunks, int kChunk, int max_levels, int* __restrict__ cnt0,
                                                     int* __restrict__ cnt1, int* __restrict__ summary) {
   const int d = blockIdx.y, b = blockIdx.x, lane = threadIdx.x;
   const int64_t* lvl = d ? lvl1 : lvl0;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kScanThreads) k_sched_scan_levels(int* cnt0, i
 
 __global__ void __launch_bounds__(32) k_sched_place(const int64_t* __restrict__ lvl0, const int64_t* __restrict__ lvl1,
                                                     const int64_t* __restrict__ nid0, const int64_t* __restrict__ nid1, int N,
-                                                    int nchunks, int max_levels, int* __restrict__ cnt0, int* __restrict__ cnt1,
+                                                    int nchunks, int kChunk, int max_levels, int* __restrict__ cnt0, int* __restrict__ cnt1,
                                                     int* __restrict__ perm0, int* __restrict__ perm1, int* __restrict__ pos0,
                                                     int* __restrict__ pos1, int* __restrict__ summary) {
   const int d = blockIdx.y, b = blockIdx.x, lane = threadIdx.x;
@@ -225,9 +226,11 @@ struct SchedWs {
   size_t bytes;
 };
 
+static int chunk_for(int64_t N) { return N <= 65536 ? kChunkSmall : kChunkBig; }
+
 static SchedWs carve(void* ws, int64_t N, int64_t E, int max_levels) {
   SchedWs w;
-  const int64_t nchunks = (N + kChunk - 1) / kChunk;
+  const int64_t nchunks = (N + chunk_for(N) - 1) / chunk_for(N);
   size_t off = 0;
   auto take = [&](int64_t n) {
     int* p = ws ? reinterpret_cast<int*>(static_cast<char*>(ws) + off) : nullptr;
@@ -268,6 +271,7 @@ extern "C" int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lv
   }
   DAGNN_REQUIRE(s->B == 0 || (batch && s->gptr), "batch / gptr");
   const int N = (int)s->N, E = (int)s->E, dirs = s->dirs, ML = s->max_levels;
+  const int kChunk = chunk_for(N);
   const int nchunks = (N + kChunk - 1) / kChunk;
   SchedWs w = carve(workspace, N, E, ML);
   if (!workspace || workspace_bytes < w.bytes) return set_err(DAGNN_E_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
@@ -279,11 +283,11 @@ extern "C" int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lv
   int *perm1 = dirs == 2 ? s->perm[1] : s->perm[0], *pos1 = dirs == 2 ? s->pos[1] : s->pos[0];
   int* rp1 = dirs == 2 ? s->rowptr[1] : s->rowptr[0];
 
-  k_sched_count<<<dim3(nchunks, dirs), 32, 0, st>>>(lvl0, lvl1, N, nchunks, ML, w.cnt[0], w.cnt[1], s->summary);
+  k_sched_count<<<dim3(nchunks, dirs), 32, 0, st>>>(lvl0, lvl1, N, nchunks, kChunk, ML, w.cnt[0], w.cnt[1], s->summary);
   if (int rc = check_launch("k_sched_count")) return rc;
   k_sched_scan_levels<<<dirs, kScanThreads, 0, st>>>(w.cnt[0], w.cnt[1], nchunks, ML, N, s->lvl_off[0], lo1, s->summary);
   if (int rc = check_launch("k_sched_scan_levels")) return rc;
-  k_sched_place<<<dim3(nchunks, dirs), 32, 0, st>>>(lvl0, lvl1, nid0, nid1, N, nchunks, ML, w.cnt[0], w.cnt[1], s->perm[0], perm1,
+  k_sched_place<<<dim3(nchunks, dirs), 32, 0, st>>>(lvl0, lvl1, nid0, nid1, N, nchunks, kChunk, ML, w.cnt[0], w.cnt[1], s->perm[0], perm1,
                                                      s->pos[0], pos1, s->summary);
   if (int rc = check_launch("k_sched_place")) return rc;
   if (E > 0) {

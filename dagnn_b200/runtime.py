@@ -96,6 +96,42 @@ def dag_levels(edge_index: torch.Tensor, num_nodes: int, max_passes: int = 257):
         passes = min(passes * 8, N + 2)
 
 
+def dvae_rows_to_tensor(rows, n: int) -> torch.Tensor:
+    """Text rows [[t0], [t1, f10], [t2, f20, f21], ...] (dvae/data/*.txt after ast.literal_eval) -> int32 [B, n, n] on the host."""
+    out = np.zeros((len(rows), n, n), dtype=np.int32)
+    for g, row in enumerate(rows):
+        if len(row) != n:
+            raise _lib.DagnnError("row %d has %d variables, expected %d" % (g, len(row), n))
+        for i, node in enumerate(row):
+            out[g, i, : len(node)] = node
+    return torch.from_numpy(out)
+
+
+def dvae_batch_from_rows(rows_dev: torch.Tensor, kind: str, nvt: int):
+    """D-VAE rows (int32 [B, n, n] on the device, `dvae_rows_to_tensor`) -> the collated batch `forward(G)` reads, built on the
+    device: decode_ENAS_to_pygraph / decode_BN_to_pygraph (dvae/util.py:343-385 / :290-339) + dvae/batch.py:26-145.
+    One D2H of the edge count at the end (edge_index is trimmed to it)."""
+    from .data import DagBatch
+    rows_dev = _req_cuda(rows_dev, "rows", torch.int32)
+    B, n = int(rows_dev.shape[0]), int(rows_dev.shape[1])
+    nn, dev = n + 2, rows_dev.device
+    N, ecap = B * nn, B * (nn * (nn - 1) // 2)
+    x = torch.empty(N, nvt, device=dev, dtype=torch.float32)
+    ei = torch.empty(2, ecap, device=dev, dtype=torch.int64)
+    bi = torch.empty(2, 2, N, device=dev, dtype=torch.int64)
+    batch = torch.empty(N, device=dev, dtype=torch.int64)
+    counts = torch.empty(4, device=dev, dtype=torch.int32)
+    nws = int(lib().dagnn_dvae_rows_workspace_bytes(B))
+    ws = torch.empty((nws + 3) // 4, device=dev, dtype=torch.int32)
+    check(lib().dagnn_dvae_rows_build(_ptr(rows_dev), B, n, 0 if kind == "NA" else 1, int(nvt), _ptr(x), _ptr(ei), ecap, _ptr(bi), _ptr(batch),
+                                      _ptr(counts), _ptr(ws), nws, _stream()), "dagnn_dvae_rows_build")
+    c = counts.cpu()
+    if int(c[1]) != 0:
+        raise _lib.DagnnError("dvae rows: a node type is outside [0, %d)" % nvt)
+    E = int(c[0])
+    return DagBatch(x=x, edge_index=ei[:, :E].contiguous(), bi_layer_index=bi, batch=batch, num_graphs=B)
+
+
 _LAYOUTS = {}      # (N, E, B, dirs, max_levels, has edge attributes) -> (offsets, total, workspace bytes) of a schedule buffer
 _LOCK = threading.Lock()     # module-level caches (_LAYOUTS, _WS): forward may run in one host thread per GPU (tg/data_parallel.py:60-61)
 

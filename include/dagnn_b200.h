@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 8
+#define DAGNN_ABI_VERSION 9
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -114,6 +114,21 @@ int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lvl0, const i
 size_t dagnn_levels_workspace_bytes(int64_t N, int32_t max_passes);
 int dagnn_levels_build(const int64_t* edge_index, int64_t N, int64_t E, int32_t max_passes, int64_t* lvl_fwd, int64_t* lvl_bwd,
                        int32_t* summary, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Input side: D-VAE text rows -> collated batch, on the device. Replaces decode_ENAS_to_pygraph / decode_BN_to_pygraph
+ * (dvae/util.py:343-385 / :290-339) and the collation of dvae/batch.py:26-145 for a batch of B rows of n variables each.
+ * rows int32 [B, n, n]: rows[g][i][0] = raw type of variable i, rows[g][i][1 + j] (j < i) = its flag for variable j (the text
+ * row [[t0], [t1, f10], [t2, f20, f21], ...] padded to n columns). kind 0 = ENAS / NA, 1 = BN. Graph g gets n + 2 nodes
+ * (start, variables, end), node ids g (n + 2) + v.
+ * Outputs (caller-allocated): x fp32 [B (n + 2), nvt] one-hot; edge_index int64 [2, ecap] (edges in the reference's order:
+ * non-zeros of the adjacency row-major, graph after graph); bi_layer_index int64 [2, 2, N] ([d][0] levels, [d][1] node ids);
+ * batch int64 [N]; counts int32 [4]: [0] = number of edges E (<= ecap or the tail was dropped: (n + 2)(n + 1) / 2 per graph
+ * is always enough), [1] = status (2: a node type outside [0, nvt)). Bit-exact integers.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t dagnn_dvae_rows_workspace_bytes(int64_t B);
+int dagnn_dvae_rows_build(const int32_t* rows, int64_t B, int32_t n, int32_t kind, int32_t nvt, float* x, int64_t* edge_index, int64_t ecap,
+                          int64_t* bi_layer_index, int64_t* batch, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Parameter packing for one (direction, layer): GRU weights -> fp16 hi/lo split, pre-swizzled shared-memory images

@@ -175,3 +175,25 @@ def test_out_of_vocabulary_index_is_loud(dev):
     g = int(B.batch[5])
     assert torch.isnan(out[g]).any()
     assert torch.isfinite(out[[k for k in range(3) if k != g]]).all()
+
+
+@pytest.mark.parametrize("fixture,kind", [("na_real_hs501", "NA"), ("bn_real_hs501", "BN")])
+def test_dvae_rows_decoded_on_device_bit_exact(fixture, kind, dev):
+    """Input side: the real NA / BN rows carried by the fixtures, decoded and collated on the device
+    (dagnn_dvae_rows_build) == the host decoders + collation (data.decode_*_row / collate_dvae, which the golden generator checked
+    against the reference's own Batch.from_data_list) — every tensor bit-exact — and the forward on it matches the fixture."""
+    import json
+    from helpers import dvae_module_from_meta, load_golden
+    from dagnn_b200 import data as D, runtime as rt
+    z, meta = load_golden(fixture)
+    rows = json.loads(str(z["rows"]))
+    n = 6 if kind == "NA" else 8
+    nvt = n + 2
+    host = D.collate_dvae([(D.decode_enas_row if kind == "NA" else D.decode_bn_row)(r) for r in rows])
+    G = rt.dvae_batch_from_rows(rt.dvae_rows_to_tensor(rows, n).to(dev), kind, nvt)
+    for k in ("x", "edge_index", "bi_layer_index", "batch"):
+        assert torch.equal(getattr(G, k).cpu(), getattr(host, k)), k
+    m = dvae_module_from_meta(meta, dev)
+    with torch.no_grad():
+        out = m(G)
+    np.testing.assert_allclose(out.cpu().numpy(), z["out"], atol=ATOL, rtol=0)
