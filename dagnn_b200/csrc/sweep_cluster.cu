@@ -212,17 +212,18 @@ __device__ __forceinline__ void store_oprow16(unsigned char* img, int nck, long 
   }
 }
 
-// x_v -> operand rows (layer 0): rows r = first, first + stride, ... of a level, two of them in flight per half-warp
-__device__ __forceinline__ void convert_x_rows(const ClusterP& P, const CDir& D, int d, int pos0, int q0, int n, int first, int stride,
-                                               int hl) {
+// x_v -> operand rows (layer 0): rows r = first, first + stride, ... of a level, NR of them in flight per half-warp
+template <int NR>
+__device__ __forceinline__ void convert_x_rows_n(const ClusterP& P, const CDir& D, int d, int pos0, int q0, int n, int first, int stride,
+                                                 int hl) {
   const int k0 = 16 * hl;
   if (k0 >= P.Kx) return;
   const int w4 = (P.Din + 3) & ~3;
-  for (int r = first; r < n; r += 2 * stride) {
-    Row16 R[2];
-    bool on[2];
+  for (int r = first; r < n; r += NR * stride) {
+    Row16 R[NR];
+    bool on[NR];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NR; ++t) {
       const int rr = r + t * stride;
       on[t] = rr < n;
       const float* src = P.X + (size_t)(on[t] ? D.perm[pos0 + rr] : 0) * P.ldx;
@@ -237,9 +238,13 @@ __device__ __forceinline__ void convert_x_rows(const ClusterP& P, const CDir& D,
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+    for (int t = 0; t < NR; ++t)
       if (on[t]) store_oprow16(P.ximg[d], P.nckx, P.Q, (long long)q0 + r + t * stride, hl, P.Kx, R[t].v);
   }
+}
+
+__device__ __forceinline__ void convert_x_rows(const ClusterP& P, const CDir& D, int d, int pos0, int q0, int n, int first, int stride, int hl) {
+  convert_x_rows_n<2>(P, D, d, pos0, q0, n, first, stride, hl);
 }
 
 // score of one in-edge apart from the key term: edge type + vertex id (constants per destination cancel)
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   unsigned char* Ring = base + kWBytes;
   CSmemTail& S = *reinterpret_cast<CSmemTail*>(Ring + (size_t)kCRingBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_entry = clock64();
   const int rank = (int)cluster_ctarank();
   const int item = (int)cluster_idx();
   const int g = item % P.G, di = item / P.G;
@@ -408,38 +414,57 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
     }
   }
 
-  // ---- weights on chip: W_hh slice -> TMEM (hi tile, lo tile), W_ih slice -> shared memory, biases
+  // ---- weights on chip: W_hh slice -> TMEM (hi tile, lo tile), W_ih slice -> shared memory, biases. The loads are issued in
+  // batches (16 independent 16-byte loads per thread in flight): done one at a time this prologue took 35 us of a 1 ms kernel.
   if (warp < 4) {
     const int gate = tid >> 5, uu = tid & 31, u = u0 + uu;
     const bool live = gate < 3 && uu < P.U && u < P.H;
     const int col = gate * P.Hq + u;
     const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
     const int nckw = P.HP >> 6;                                 // k chunks of the packed W_hh image (Kh64 / 64)
-    for (int ks = 0; ks < P.Kh / 16; ++ks) {
-      uint32_t wh[8], wl[8];
+    const int nks = P.Kh / 16;
+    for (int ks0 = 0; ks0 < nks; ks0 += 4) {
+      uint4 wv[4][4];                                           // [k step][hi granule 0, hi granule 1, lo granule 0, lo granule 1]
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { wh[j] = 0u; wl[j] = 0u; }
-      if (live) {
-        const uint4 h0 = packed_w8(Lp.w_hh, nckw, col, 2 * ks, 0), h1 = packed_w8(Lp.w_hh, nckw, col, 2 * ks + 1, 0);
-        const uint4 l0 = packed_w8(Lp.w_hh, nckw, col, 2 * ks, 1), l1 = packed_w8(Lp.w_hh, nckw, col, 2 * ks + 1, 1);
-        wh[0] = h0.x; wh[1] = h0.y; wh[2] = h0.z; wh[3] = h0.w; wh[4] = h1.x; wh[5] = h1.y; wh[6] = h1.z; wh[7] = h1.w;
-        wl[0] = l0.x; wl[1] = l0.y; wl[2] = l0.z; wl[3] = l0.w; wl[4] = l1.x; wl[5] = l1.y; wl[6] = l1.z; wl[7] = l1.w;
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[q][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (live && ks0 + q < nks) {
+          wv[q][0] = packed_w8(Lp.w_hh, nckw, col, 2 * (ks0 + q), 0); wv[q][1] = packed_w8(Lp.w_hh, nckw, col, 2 * (ks0 + q) + 1, 0);
+          wv[q][2] = packed_w8(Lp.w_hh, nckw, col, 2 * (ks0 + q), 1); wv[q][3] = packed_w8(Lp.w_hh, nckw, col, 2 * (ks0 + q) + 1, 1);
+        }
       }
-      tc::st8(taddr + (uint32_t)(kColWhi + 8 * ks), wh);
-      tc::st8(taddr + (uint32_t)(kColWlo + 8 * ks), wl);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (ks0 + q < nks) {                                    // warp-uniform
+          const uint32_t wh[8] = {wv[q][0].x, wv[q][0].y, wv[q][0].z, wv[q][0].w, wv[q][1].x, wv[q][1].y, wv[q][1].z, wv[q][1].w};
+          const uint32_t wl[8] = {wv[q][2].x, wv[q][2].y, wv[q][2].z, wv[q][2].w, wv[q][3].x, wv[q][3].y, wv[q][3].z, wv[q][3].w};
+          tc::st8(taddr + (uint32_t)(kColWhi + 8 * (ks0 + q)), wh);
+          tc::st8(taddr + (uint32_t)(kColWlo + 8 * (ks0 + q)), wl);
+        }
+      }
     }
     tc::wait_st();
   } else {
-    const int t = tid - 128, nt = kCThreads - 128;
-    const int ngr = nck_in * 8;                                 // 16-byte granules per row
-    for (int idx = t; idx < 2 * kWRows * ngr; idx += nt) {
-      const int gk = idx % ngr, r = (idx / ngr) % kWRows, plane = idx / (ngr * kWRows);
+    // 192 threads = 2 planes x 96 rows of the W_ih slice: a thread copies its row, 8 granules in flight
+    const int t = tid - 128;
+    if (t < 2 * kWRows) {
+      const int plane = t / kWRows, r = t - plane * kWRows;
       const int gate = r >> 5, uu = r & 31, u = u0 + uu;
-      uint4 w = make_uint4(0u, 0u, 0u, 0u);
-      if (uu < P.U && u < P.H && 8 * gk < Kin) w = packed_w8(Lp.w_ih, Lp.ih_nck, Lp.ih_col0 + gate * P.Hq + u, gk, plane);
-      *reinterpret_cast<uint4*>(Wih + ((size_t)plane * nck_in + (gk >> 3)) * kWChunkBytes + tc::tile_off(r, gk & 7)) = w;
+      const bool live = uu < P.U && u < P.H;
+      const int colw = Lp.ih_col0 + gate * P.Hq + u;
+      const int ngr = nck_in * 8;                               // 16-byte granules per row
+      for (int g0 = 0; g0 < ngr; g0 += 8) {
+        uint4 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          w[j] = (live && 8 * (g0 + j) < Kin) ? packed_w8(Lp.w_ih, Lp.ih_nck, colw, g0 + j, plane) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(Wih + ((size_t)plane * nck_in + ((g0 + j) >> 3)) * kWChunkBytes + tc::tile_off(r, (g0 + j) & 7)) = w[j];
+      }
     }
-    for (int idx = t; idx < 4 * kCU; idx += nt) {
+    for (int idx = t; idx < 4 * kCU; idx += kCThreads - 128) {
       const int b = idx / kCU, uu = idx % kCU, u = u0 + uu;
       S.bias[b][uu] = (uu < P.U && u < P.HP) ? __ldg(Lp.bias + (size_t)b * P.HP + u) : 0.f;
     }
@@ -467,11 +492,15 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
   // layer 0: the operand rows of level 0's inputs (those of level l + 1 are converted during level l)
   if (first_layer && L > 0) {
     const int4 T0 = __ldcg(tab);
-    if (warp < kCWorkWarps) convert_x_rows(P, D, d, T0.x, T0.z, T0.y, ghw, kHalfWarps, hl);
+    if (warp < kCWorkWarps) convert_x_rows_n<4>(P, D, d, T0.x, T0.z, T0.y, ghw, kHalfWarps, hl);
     asm volatile("fence.proxy.async.global;" ::: "memory");
     cluster_sync_all();
   }
 
+  if (P.trace && tid == 0 && L < P.max_levels) {       // kernel-level stamps in the entry behind the last level: entry, prologue done
+    long long* tk = P.trace + (((size_t)L * 256 + blockIdx.x) << 4);
+    tk[0] = t_entry; tk[1] = clock64();
+  }
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const int4 T = __ldcg(tab + l);
@@ -800,7 +829,7 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
         const int ghw_s = (((lane >> 4) * (kCWorkWarps / 2) + (warp & 3)) * kCS + rank);      // half-warp index among 64
         if (split && warp >= kCWorkWarps / 2) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw_s, kHalfWarps / 2, hl);
         if (exchange) gather_rows(split ? (warp < kCWorkWarps / 2 ? ghw_s : n) : ghw, split ? kHalfWarps / 2 : kHalfWarps, n);
-        if (first_layer && !split && Tn.y > 0) convert_x_rows(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
+        if (first_layer && !split && Tn.y > 0) convert_x_rows_n<4>(P, D, d, Tn.x, Tn.z, Tn.y, ghw, kHalfWarps, hl);   // next level's input rows
       }
     } else if (warp == kCopyWarp) {
       copy_stages(early);

@@ -58,3 +58,14 @@ for c in range(items * G_):
     print("    sum of level durations %.1f us" % tot)
 end = tr[:L, :ncta, 4].max()
 print("first start -> last close: %.1f us" % ((end - t00) / MHZ))
+k0 = tr[L, :ncta, 0]
+print("kernel entry (earliest CTA) -> last close: %.1f us; prologue (weights on chip, tables, level-0 input rows) per cluster, us:" % ((end - k0.min()) / MHZ))
+for c in range(items * G_):
+    cta = 8 * c
+    g, di = c % G_, c // G_
+    i, d = di // dirs, di % dirs
+    lv = tr[:L, cta, :]
+    done = lv[:, 4].max()
+    print("  cluster %2d (layer %d dir %d group %d): entry +%.1f, prologue %.1f, first level starts +%.1f, last level closes +%.1f" % (
+        c, i, d, g, (tr[L, cta, 0] - k0.min()) / MHZ, (tr[L, cta:cta + 8, 1].max() - tr[L, cta, 0]) / MHZ,
+        (lv[0, 0] - k0.min()) / MHZ, (done - k0.min()) / MHZ))
