@@ -431,11 +431,11 @@ def main():
             "metric": "graphs/sec forward", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": total_graphs,
-                       "nodes_rank0": N, "edges_rank0": int(Bcpu.edge_index.shape[1]), "levels": int(sched.num_levels[0]),
-                       "l2": "flushed between steps (256 MiB fill)" if not args.no_flush else "not flushed",
-                       "timed_region": "node encoder + schedule build (incl. its one D2H of level offsets) + level sweeps + readout",
-                       "parallelism": "graph-sharded dp%d (depth-aware shards), no forward collective" % world},
+            "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": total_graphs},
+            "details": {"nodes_rank0": N, "edges_rank0": int(Bcpu.edge_index.shape[1]), "levels": int(sched.num_levels[0]),
+                        "l2": "flushed between steps (256 MiB fill)" if not args.no_flush else "not flushed",
+                        "timed_region": "node encoder + schedule build (incl. its one D2H of level offsets) + level sweeps + readout",
+                        "parallelism": "graph-sharded dp%d (depth-aware shards), no forward collective" % world},
             "e2e": {"value": e2e, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

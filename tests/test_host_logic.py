@@ -86,6 +86,17 @@ def test_depth_aware_sharding_spreads_deep_graphs_and_balances_modelled_cost():
     assert sum(p is not None for p in parts) == 2 and sum(p.num_graphs for p in parts if p is not None) == 2
 
 
+def test_dvae_rows_to_tensor_layout():
+    """Text rows -> the int32 [B, n, n] layout dagnn_dvae_rows_build reads (type in column 0, flags behind it, zero padded)."""
+    from dagnn_b200 import runtime as rt, _lib
+    rows = [[[3], [1, 0], [5, 1, 1]], [[0], [2, 1], [4, 0, 1]]]
+    t = rt.dvae_rows_to_tensor(rows, 3)
+    assert t.dtype == torch.int32 and tuple(t.shape) == (2, 3, 3)
+    assert t[0].tolist() == [[3, 0, 0], [1, 0, 0], [5, 1, 1]] and t[1].tolist() == [[0, 0, 0], [2, 1, 0], [4, 0, 1]]
+    with pytest.raises(_lib.DagnnError):
+        rt.dvae_rows_to_tensor([[[1]]], 3)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
