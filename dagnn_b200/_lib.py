@@ -19,7 +19,7 @@ HEADERS = ["common.cuh", "sync.cuh", "tc.cuh"]
 MAX_LAYERS = 8
 MAX_DIRS = 2
 MAX_READOUT_BLOCKS = 20
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 vp = C.c_void_p
 
@@ -30,7 +30,7 @@ class DagnnSchedule(C.Structure):
         ("dirs", C.c_int32), ("max_levels", C.c_int32),
         ("perm", vp * MAX_DIRS), ("pos", vp * MAX_DIRS), ("lvl_off", vp * MAX_DIRS), ("rowptr", vp * MAX_DIRS),
         ("col", vp * MAX_DIRS), ("eid", vp * MAX_DIRS), ("eattr", vp * MAX_DIRS),
-        ("gptr", vp), ("summary", vp),
+        ("gptr", vp), ("gdepth", vp), ("summary", vp),
     ]
 
 

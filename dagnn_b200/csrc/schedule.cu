@@ -202,12 +202,19 @@ __global__ void __launch_bounds__(256) k_sched_rows(const int64_t* __restrict__ 
   }
 }
 
-__global__ void k_sched_gptr(const int64_t* __restrict__ batch, int N, int B, int* __restrict__ gptr, int* __restrict__ summary) {
+// graph pointers (first node id of every graph) and, optionally, the number of levels of every graph (gdepth, zeroed by the
+// launcher: max forward level + 1 — the cluster sweep balances its graph groups with it)
+__global__ void k_sched_gptr(const int64_t* __restrict__ batch, const int64_t* __restrict__ lvl0, int N, int B, int max_levels,
+                             int* __restrict__ gptr, int* __restrict__ gdepth, int* __restrict__ summary) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= N; v += gridDim.x * blockDim.x) {
     long long cur = (v < N) ? batch[v] : B;
     long long prev = (v > 0) ? batch[v - 1] : -1;
     if (cur < prev || cur > B || (v < N && cur >= B)) { summary[2] = 2; continue; }
     for (long long g = prev + 1; g <= cur; ++g) gptr[g] = v;
+    if (gdepth && v < N) {
+      const long long l = lvl0[v];
+      if (l >= 0 && l < max_levels) atomicMax(&gdepth[cur], (int)l + 1);
+    }
   }
 }
 
@@ -310,7 +317,8 @@ extern "C" int dagnn_schedule_build(const int64_t* edge_index, const int64_t* lv
     if (int rc = check_launch("k_sched_rows")) return rc;
   }
   if (s->B > 0) {
-    k_sched_gptr<<<min(1184, ceil_div(N + 1, 256)), 256, 0, st>>>(batch, N, (int)s->B, s->gptr, s->summary);
+    if (s->gdepth) DAGNN_CUDA_OK(cudaMemsetAsync(s->gdepth, 0, (size_t)s->B * sizeof(int), st));
+    k_sched_gptr<<<min(1184, ceil_div(N + 1, 256)), 256, 0, st>>>(batch, lvl0, N, (int)s->B, ML, s->gptr, s->gdepth, s->summary);
     if (int rc = check_launch("k_sched_gptr")) return rc;
   }
   return DAGNN_OK;

@@ -81,6 +81,7 @@ struct ClusterP {
   unsigned char* ximg[DAGNN_MAX_DIRS];   // operand rows of X in the position order of each direction
   const int* summary;          // [0] levels, [2] status, [3] node ids are not the identity
   const int* gptr;             // [B+1]
+  const int* gdepth;           // [B] levels of every graph, or nullptr
   int4* tab;                   // [items][max_levels + 1] per level: first position, rows, first operand row, level start
   unsigned int* flags;         // [2][kCMaxItems][8] per CTA of every cluster: projection chunks whose states it has published; chunks
                                // whose aggregates it has gathered (pipelined levels)
@@ -385,10 +386,54 @@ __global__ void __launch_bounds__(kCThreads, 1) k_sweep_cluster(const __grid_con
 
   // ---- level table of this (direction, group): CTA 0 of the cluster builds it, the cluster barrier below publishes it
   if (rank == 0 && L > 0) {
+    // Graph groups = G consecutive ranges of graphs. A cluster's time is ~ levels x t_level + nodes x t_node (measured: 6.7 us
+    // per level, 0.081 us per node: one level costs what kLevelNodes nodes cost), so the cuts minimise the largest
+    // kLevelNodes x (deepest graph of the group) + (nodes of the group): every cluster derives the same cuts from the graph
+    // pointers and depths (32-ary search on the bound, greedy feasibility scan per lane). Without depths: equal node counts.
+    constexpr int kLevelNodes = 80, kMaxBalanced = 3000;
     int gb_lo = 0, gb_hi = P.N;
     if (P.G > 1) {
       if (P.summary[3] != 0) {                  // level arrays with their own node ids: no order to cut groups by
         if (g > 0) gb_lo = P.N;
+      } else if (P.gdepth != nullptr && P.B <= kMaxBalanced) {
+        int* sg = reinterpret_cast<int*>(&S.stage[0][0][0]);      // [B + 1] graph pointers, [B] depths (the stage is idle here)
+        int* sd = sg + P.B + 1;
+        int* sb = sd + P.B;                                        // [G + 1] cuts (graph indices)
+        for (int k = tid; k <= P.B; k += kCThreads) sg[k] = P.gptr[k];
+        for (int k = tid; k < P.B; k += kCThreads) sd[k] = P.gdepth[k];
+        __syncthreads();
+        if (warp == 0) {
+          auto groups_needed = [&](int T, bool emit) {
+            int groups = 1, nn = 0, dd = 0;
+            if (emit) sb[0] = 0;
+#pragma unroll 8
+            for (int k = 0; k < P.B; ++k) {                        // (the loads do not depend on the running state: they pipeline)
+              const int nk = sg[k + 1] - sg[k], dk = sd[k];
+              const int n2 = nn + nk, d2 = max(dd, dk);
+              if (nn > 0 && kLevelNodes * d2 + n2 > T) {
+                if (emit && groups <= P.G) sb[groups] = k;
+                ++groups; nn = nk; dd = dk;
+              } else { nn = n2; dd = d2; }
+            }
+            if (emit) for (int q = groups; q <= P.G; ++q) sb[q] = P.B;
+            return groups;
+          };
+          int lo = 0, hi = kLevelNodes * L + P.N;                  // feasible at hi (one group), infeasible below every single graph's cost
+          for (int round = 0; round < 3 && hi - lo > 8; ++round) {      // to within 8 nodes' worth of cost
+            const int step = max(1, (hi - lo + 31) / 32);
+            const int T = min(hi, lo + step * (lane + 1));
+            const bool okT = groups_needed(T, false) <= P.G;
+            const unsigned m = __ballot_sync(0xffffffffu, okT);       // monotone: feasible from some lane on
+            const int first = m ? __ffs(m) - 1 : 31;
+            const int nhi = min(hi, lo + step * (first + 1)), nlo = first == 0 ? lo : min(hi, lo + step * first);
+            hi = nhi; lo = nlo;
+          }
+          if (lane == 0) groups_needed(hi, true);
+        }
+        __syncthreads();
+        gb_lo = sg[sb[g]];
+        gb_hi = g + 1 == P.G ? P.N : sg[sb[g + 1]];
+        __syncthreads();
       } else {
         const long long t0 = (long long)P.N * g / P.G, t1 = (long long)P.N * (g + 1) / P.G;
         gb_lo = g == 0 ? 0 : P.gptr[lower_bound_dev(P.gptr, P.B + 1, (int)t0)];
@@ -945,7 +990,7 @@ int cluster_forward(const DagnnSweepArgs* A, cudaStream_t st, bool* handled) {
   P.vec_x = ((A->ldx & 3) == 0 && (A->Din & 3) == 0 && ((uintptr_t)A->X & 15) == 0) ? 1 : 0;
   P.max_levels = S->max_levels;
   P.ldh = A->ldh; P.ldx = A->ldx; P.Q = cluster_q_rows(S->N, S->max_levels, dirs, layers);
-  P.X = A->X; P.summary = S->summary; P.gptr = S->gptr;
+  P.X = A->X; P.summary = S->summary; P.gptr = S->gptr; P.gdepth = S->gdepth;
   P.trace = static_cast<long long*>(A->trace);
   char* ws = static_cast<char*>(A->workspace);
   P.flags = reinterpret_cast<unsigned int*>(ws); ws += 1024;

@@ -181,6 +181,7 @@ class Schedule(object):
                 if edge_attr is not None:
                     sizes.append(("eattr%d" % d, 2 * E))
             sizes.append(("gptr", B + 1))
+            sizes.append(("gdepth", B))
             offs, tot = {}, 0
             for k, n in sizes:
                 offs[k] = tot
@@ -207,6 +208,7 @@ class Schedule(object):
             c.rowptr[d], c.col[d], c.eid[d] = addr("rowptr%d" % d), addr("col%d" % d), addr("eid%d" % d)
             c.eattr[d] = addr("eattr%d" % d) if edge_attr is not None else None
         c.gptr = addr("gptr")
+        c.gdepth = addr("gdepth")
         ws_ptr = base + 4 * tot
         check(lib().dagnn_schedule_build(_ptr(edge_index), _ptr(levels[0]), _ptr(levels[1]) if dirs == 2 else None,
                                          _ptr(node_ids[0]), _ptr(node_ids[1]) if dirs == 2 else None,

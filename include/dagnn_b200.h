@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DAGNN_ABI_VERSION 9
+#define DAGNN_ABI_VERSION 10
 #define DAGNN_MAX_LAYERS 8          /* stacked GRU layers per direction                         */
 #define DAGNN_MAX_DIRS 2            /* 0 = forward sweep, 1 = sweep on the reversed DAG          */
 #define DAGNN_K_CHUNK 64            /* K granularity of the packed weight images (one swizzle row of fp16) */
@@ -84,6 +84,8 @@ typedef struct DagnnSchedule {
   int32_t* eid[DAGNN_MAX_DIRS];     /* [E]   original edge id (ascending inside a row)         */
   float* eattr[DAGNN_MAX_DIRS];     /* [E,2] edge_attr rows in CSR order, or NULL              */
   int32_t* gptr;                    /* [B+1] first node id of each graph (batch vector sorted) */
+  int32_t* gdepth;                  /* [B]   number of levels of each graph (max forward level + 1), or NULL: the cluster sweep
+                                             then cuts its graph groups by node count alone                         */
   /* summary[0]=num_levels of dir 0, [1]=num_levels of dir 1, [2]=status (0 ok, 1 level >= max_levels,
    * 2 node id / edge endpoint out of range), [3] = 1 when a level array carries node ids other than 0..N-1 in order
    * (positions inside a level are then not sorted by node id), [4..7] reserved.                       */

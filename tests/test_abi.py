@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound(built_lib):
         assert hasattr(raw, name), "libdagnn_sm100.so does not export %s" % name
         assert name in _lib.EXPORTS, "%s is declared in the header but has no ctypes binding" % name
     assert sorted(_lib.EXPORTS) == declared
-    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 9
+    assert built_lib.dagnn_abi_version() == _lib.ABI_VERSION == 10
 
 
 def test_pack_layout_and_workspace_queries(built_lib):
